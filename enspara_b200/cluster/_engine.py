@@ -1,0 +1,190 @@
+"""Host driver of the fused k-centers device loop.
+
+One iteration of the reference (/root/reference/enspara/cluster/kcenters.py:243-311 serial,
+:314-378 per shard) is ONE kernel launch here (csrc/eb_rmsd_kcenters.cu, csrc/eb_feat.cu), plus
+ONE all-gather of candidate records when frames are sharded over ranks.  The winner of the
+cross-shard arg-max is chosen on the device by the next launch's prologue, so the host never
+waits for it: launches are queued in batches and only a 64-byte state block is read back per
+batch to learn whether the stop rule (kcenters.py:217) fired.
+"""
+import numpy as np
+import torch
+
+from .. import _lib
+from ..device import DeviceFeatures, DeviceTrajectory, ptr, stream_ptr
+
+_INT32_MAX = 2 ** 31 - 1
+
+
+class ShardInfo:
+    """Where this rank's frames sit in the global order: contiguous blocks by rank, so that
+    'lowest rank, then lowest local index' (kcenters.py:337-338) == lowest global index."""
+
+    def __init__(self, n_local, comm):
+        self.comm = comm
+        self.size = comm.size
+        self.rank = comm.rank
+        lens = comm.all_gather_object(int(n_local))
+        self.lengths = np.asarray(lens, dtype=np.int64)
+        self.offsets = np.concatenate([[0], np.cumsum(self.lengths)]).astype(np.int64)
+        self.offset = int(self.offsets[self.rank])
+        self.n_global = int(self.offsets[-1])
+
+    def to_rank_local(self, global_idx):
+        r = int(np.searchsorted(self.offsets, global_idx, side="right") - 1)
+        return r, int(global_idx - self.offsets[r])
+
+
+class KCentersEngine:
+    """Device state of one k-centers run over one shard."""
+
+    #: launches queued between two reads of the state block when a distance cutoff is active
+    POLL_EVERY = 32
+
+    def __init__(self, data, metric_kind, comm, exact=True):
+        self.data = data
+        self.kind = metric_kind
+        self.comm = comm
+        self.exact = bool(exact)
+        self.lib = _lib.load()
+        self.n = len(data)
+        self.shard = ShardInfo(self.n, comm)
+        self.is_rmsd = isinstance(data, DeviceTrajectory)
+        dev = data.xyz.device if self.is_rmsd else data.X.device
+        self.dev = dev
+        if self.is_rmsd:
+            self.rec_bytes = int(self.lib.eb_rmsd_record_bytes(data.n_atoms))
+            self.dist = torch.full((self.n,), float("inf"), dtype=torch.float32, device=dev)
+        else:
+            self.rec_bytes = int(self.lib.eb_feat_record_bytes(data.n_features, data.dt))
+            self.dist = torch.full((self.n,), float("inf"), dtype=torch.float64, device=dev)
+        self.assign = torch.full((self.n,), -1, dtype=torch.int32, device=dev)
+        self.state = torch.zeros(64, dtype=torch.uint8, device=dev)
+        self.partials = torch.empty(int(self.lib.eb_kc_partials_bytes()), dtype=torch.uint8,
+                                    device=dev)
+        self.cand_out = torch.zeros(self.rec_bytes, dtype=torch.uint8, device=dev)
+        if self.shard.size > 1:
+            self.cand_all = torch.zeros(self.rec_bytes * self.shard.size, dtype=torch.uint8,
+                                        device=dev)
+        else:
+            self.cand_all = self.cand_out
+        self.center_list = None
+        self._state_host = torch.empty(64, dtype=torch.uint8).pin_memory()
+        self.launches = 0
+
+    # -- state ---------------------------------------------------------------------------
+    def set_state(self, distances, assignments):
+        """Warm start (kcenters.py:200-206): take over existing distances / assignments."""
+        self.dist.copy_(torch.as_tensor(np.asarray(distances), device=self.dev).to(
+            self.dist.dtype))
+        self.assign.copy_(torch.as_tensor(np.asarray(assignments), device=self.dev).to(
+            torch.int32))
+
+    def read_state(self):
+        self._state_host.copy_(self.state, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return _lib.KcState.from_buffer_copy(self._state_host.numpy().tobytes())
+
+    # -- launches ------------------------------------------------------------------------
+    def _exchange(self):
+        if self.shard.size > 1:
+            self.comm.all_gather_into(self.cand_all, self.cand_out)
+
+    def seed(self, first_center_id=0):
+        s = stream_ptr()
+        if self.is_rmsd:
+            d = self.data
+            _lib.call("eb_kcenters_seed_rmsd", ptr(d.xyz), ptr(d.traces), self.n, d.n_atoms,
+                      self.shard.offset, ptr(self.dist), int(first_center_id), ptr(self.state),
+                      ptr(self.partials), ptr(self.cand_out), s)
+        else:
+            d = self.data
+            _lib.call("eb_kcenters_seed_feat", ptr(d.X), self.n, d.n_features, d.dt,
+                      self.shard.offset, ptr(self.dist), int(first_center_id), ptr(self.state),
+                      ptr(self.partials), ptr(self.cand_out), s)
+        self.launches += 1
+        self._exchange()
+
+    def step(self, n_clusters_limit, cutoff):
+        s = stream_ptr()
+        d = self.data
+        if self.is_rmsd:
+            _lib.call("eb_kcenters_step_rmsd", ptr(d.xyz), ptr(d.traces), self.n, d.n_atoms,
+                      self.shard.offset, ptr(self.cand_all), self.shard.size, ptr(self.dist),
+                      ptr(self.assign), n_clusters_limit, float(cutoff), ptr(self.state),
+                      ptr(self.center_list), ptr(self.partials), ptr(self.cand_out),
+                      int(self.exact), s)
+        else:
+            _lib.call("eb_kcenters_step_feat", ptr(d.X), self.n, d.n_features, d.dt,
+                      _lib_metric(self.kind), self.shard.offset, ptr(self.cand_all),
+                      self.shard.size, ptr(self.dist), ptr(self.assign), n_clusters_limit,
+                      float(cutoff), ptr(self.state), ptr(self.center_list),
+                      ptr(self.partials), ptr(self.cand_out), s)
+        self.launches += 1
+        self._exchange()
+
+    def _ensure_center_list(self, capacity):
+        if self.center_list is None or self.center_list.numel() < capacity:
+            new = torch.full((capacity,), -1, dtype=torch.int64, device=self.dev)
+            if self.center_list is not None:
+                new[:self.center_list.numel()].copy_(self.center_list)
+            self.center_list = new
+
+    def run(self, n_clusters, dist_cutoff, n_existing=0, on_progress=None):
+        """Run until the reference's stop rule fires (kcenters.py:217).  ``n_existing`` centres
+        (init_centers) already count towards ``n_clusters`` and shift the new centre ids.
+        Returns (global frame indices of the centres chosen by this run, final global max of
+        min-distances)."""
+        n_global = self.shard.n_global
+        if n_clusters is None or n_clusters == np.inf:
+            limit = _INT32_MAX
+        else:
+            limit = int(min(int(n_clusters), _INT32_MAX))
+        cutoff = 0.0 if dist_cutoff is None else float(dist_cutoff)
+        self.seed(n_existing)
+        if limit <= n_existing or n_global == 0:
+            return [], self._global_maxdist()
+        bounded = limit < _INT32_MAX
+        # the centre list grows geometrically when only a cutoff bounds the run; a run can
+        # never choose more new centres than there are frames
+        hard_cap = n_existing + n_global
+        capacity = min(limit, hard_cap) if bounded else min(hard_cap, n_existing + 4096)
+        self._ensure_center_list(capacity)
+        queued = n_existing          # centre ids for which a launch has been queued
+        while True:
+            if bounded and cutoff <= 0.0:
+                batch = limit - queued
+            else:
+                batch = min(self.POLL_EVERY, limit - queued)
+            if queued + batch > self.center_list.numel():
+                self._ensure_center_list(min(hard_cap, max(2 * self.center_list.numel(),
+                                                           queued + batch)))
+                batch = min(batch, self.center_list.numel() - queued)
+            for _ in range(batch):
+                self.step(limit, cutoff)
+            queued += batch
+            st = self.read_state()
+            if on_progress is not None:
+                on_progress(st)
+            if st.done or st.n_centers >= limit or queued >= hard_cap or batch <= 0:
+                break
+        k = int(st.n_centers)
+        centers = self.center_list[n_existing:k].cpu().numpy().astype(np.int64)
+        return [int(c) for c in centers], self._global_maxdist()
+
+    def _global_maxdist(self):
+        st = self.read_state()
+        t = torch.tensor([st.local_maxdist], dtype=torch.float64, device=self.dev)
+        self.comm.all_reduce_max(t)
+        return float(t.cpu()[0])
+
+    # -- results -------------------------------------------------------------------------
+    def results_host(self):
+        """(assignments int64, distances float64) like kcenters.py:198-199."""
+        return (self.assign.cpu().numpy().astype(np.int64),
+                self.dist.cpu().numpy().astype(np.float64))
+
+
+def _lib_metric(kind):
+    return {"euclidean": _lib.METRIC_EUCLIDEAN, "manhattan": _lib.METRIC_MANHATTAN,
+            "sqeuclidean": _lib.METRIC_SQEUCLIDEAN}[kind]

@@ -1,0 +1,141 @@
+"""Host wrappers around the one-vs-all and many-centres kernels.
+
+Everything here enqueues work through the C ABI (enspara_b200/_lib.py) on torch's current
+stream and returns host numpy arrays shaped and typed like the reference's.
+"""
+import numpy as np
+import torch
+
+from .. import _lib
+from ..device import DeviceFeatures, DeviceTrajectory, ptr, stream_ptr
+from ..exception import DataInvalid
+
+
+def _single_frame_soa(metric, y, like):
+    """One datum -> device (SoA coords, trace) for RMSD, or a device row for features."""
+    if metric.is_rmsd:
+        if isinstance(y, DeviceTrajectory):
+            if len(y) != 1:
+                raise DataInvalid("expected a single frame, got %d" % len(y))
+            return y
+        xyz = np.asarray(y.xyz if hasattr(y, "xyz") else y, dtype=np.float32)
+        if xyz.ndim == 2:
+            xyz = xyz[None]
+        if xyz.shape[0] != 1:
+            xyz = xyz[:1]
+        if xyz.shape[1] != like.n_atoms:
+            raise DataInvalid("centre has %d atoms, data has %d" % (xyz.shape[1], like.n_atoms))
+        return DeviceTrajectory.from_host(xyz)
+    arr = np.asarray(y)
+    if arr.ndim != 1:
+        raise DataInvalid("Target point dimension must be one, got shape %s." % (arr.shape,))
+    if arr.shape[0] != like.n_features:
+        raise DataInvalid("Target data point dimension (%s) must match data array dimension "
+                          "(%s)" % (arr.shape[0], like.n_features))
+    if arr.dtype != like.np_dtype:
+        raise ValueError("Buffer dtype mismatch, expected '%s' but got '%s'"
+                         % (like.np_dtype, arr.dtype))
+    return DeviceFeatures.from_host(arr[None])
+
+
+def one_to_all_device(metric, data, center, exact=True):
+    """Distances of every frame of ``data`` to ``center`` as a device tensor
+    (float32 for RMSD like md.rmsd, float64 for libdist metrics)."""
+    n = len(data)
+    if metric.is_rmsd:
+        out = torch.empty(n, dtype=torch.float32, device=data.xyz.device)
+        _lib.call("eb_rmsd_one_to_all", ptr(data.xyz), ptr(data.traces), n, data.n_atoms,
+                  ptr(center.xyz), _trace0(center),
+                  ptr(out), int(exact), stream_ptr())
+        return out
+    out = torch.empty(n, dtype=torch.float64, device=data.X.device)
+    from ._engine import _lib_metric
+    _lib.call("eb_feat_one_to_all", ptr(data.X), n, data.n_features, data.dt,
+              _lib_metric(metric.kind), ptr(center.X), ptr(out), stream_ptr())
+    return out
+
+
+def _trace0(center):
+    # a 1-element D2H; only used on the convenience one-vs-all path, never in the device loops
+    return float(center.traces[:1].cpu()[0])
+
+
+def one_to_all(metric, X, y, out=None):
+    """The metric-callable protocol ``d = f(X, y)`` (cluster/util.py:289-313)."""
+    data = metric.to_device(X)
+    center = _single_frame_soa(metric, y, data)
+    d = one_to_all_device(metric, data, center).cpu().numpy()
+    if out is not None:
+        if out.dtype != np.float64:
+            raise DataInvalid("In-place output array must be np.float64, got '%s'." % out.dtype)
+        if out.ndim != 1:
+            raise DataInvalid("In-place output array must be one-dimensional, got shape %s"
+                              % (out.shape,))
+        if out.shape[0] != len(data):
+            raise DataInvalid("In-place output array dimension (%s) must match number of "
+                              "samples in data array (%s)" % (out.shape[0], len(data)))
+        out[:] = d
+        return out
+    return d
+
+
+def centers_to_device(metric, cluster_centers, like):
+    """An iterable of centres (list of 1-frame trajectories / rows, a Trajectory, an array)
+    -> one dense device container."""
+    if isinstance(cluster_centers, (DeviceTrajectory, DeviceFeatures)):
+        return cluster_centers
+    if metric.is_rmsd:
+        if hasattr(cluster_centers, "xyz"):
+            xyz = np.asarray(cluster_centers.xyz, dtype=np.float32)
+        else:
+            frames = []
+            for c in cluster_centers:
+                a = np.asarray(c.xyz if hasattr(c, "xyz") else c, dtype=np.float32)
+                frames.append(a[0] if a.ndim == 3 else a)
+            xyz = np.stack(frames) if frames else np.zeros((0, like.n_atoms, 3), np.float32)
+        if xyz.ndim != 3 or xyz.shape[1] != like.n_atoms:
+            raise DataInvalid("cluster centres have shape %s, data has %d atoms"
+                              % (xyz.shape, like.n_atoms))
+        return DeviceTrajectory.from_host(xyz)
+    arr = np.asarray([np.asarray(c) for c in cluster_centers]) \
+        if not isinstance(cluster_centers, np.ndarray) else cluster_centers
+    if arr.ndim != 2 or arr.shape[1] != like.n_features:
+        raise DataInvalid("cluster centres have shape %s, data has %d features"
+                          % (arr.shape, like.n_features))
+    if arr.dtype != like.np_dtype:
+        raise ValueError("Buffer dtype mismatch, expected '%s' but got '%s'"
+                         % (like.np_dtype, arr.dtype))
+    return DeviceFeatures.from_host(arr)
+
+
+def assign_device(metric, data, centers, frame_idx=None, out_dist=None, out_assign=None,
+                  accumulate=False):
+    """Nearest-centre pass on the device.  Returns (dist tensor, assign int32 tensor)."""
+    n = len(data)
+    dev = data.xyz.device if metric.is_rmsd else data.X.device
+    m = n if frame_idx is None else int(frame_idx.numel())
+    k = len(centers)
+    dt = torch.float32 if metric.is_rmsd else torch.float64
+    if out_dist is None:
+        out_dist = torch.full((m,), float("inf"), dtype=dt, device=dev)
+        out_assign = torch.zeros((m,), dtype=torch.int32, device=dev)
+    if m == 0 or k == 0:
+        return out_dist, out_assign
+    if metric.is_rmsd:
+        _lib.call("eb_rmsd_assign", ptr(data.xyz), ptr(data.traces), n, data.n_atoms,
+                  ptr(centers.xyz), ptr(centers.traces), k, ptr(frame_idx), m, ptr(out_dist),
+                  ptr(out_assign), int(accumulate), stream_ptr())
+    else:
+        from ._engine import _lib_metric
+        _lib.call("eb_feat_assign", ptr(data.X), n, data.n_features, data.dt,
+                  _lib_metric(metric.kind), ptr(centers.X), k, ptr(frame_idx), m,
+                  ptr(out_dist), ptr(out_assign), int(accumulate), stream_ptr())
+    return out_dist, out_assign
+
+
+def assign_host(metric, trajectory, cluster_centers):
+    """assign_to_nearest_center (cluster/util.py:159-205) -> (int64[n], float64[n]) numpy."""
+    data = metric.to_device(trajectory)
+    centers = centers_to_device(metric, cluster_centers, data)
+    d, a = assign_device(metric, data, centers)
+    return a.cpu().numpy().astype(np.int64), d.cpu().numpy().astype(np.float64)

@@ -1,0 +1,447 @@
+// K5 (centring + trace, AoS -> SoA) and K1 (fused RMSD k-centers step) for sm_100a.
+//
+// Reference behaviour reproduced (paths under /root/reference/enspara/):
+//   cluster/kcenters.py:243-311  _kcenters_iteration      (argmax, distance, strict-< update)
+//   cluster/kcenters.py:314-378  _kcenters_iteration_mpi  (cross-shard argmax, centre bcast)
+//   cluster/kcenters.py:217      stop rule
+//   mdtraj.rmsd (third party)    centring, traces, Theobald QCP  
+//
+// Design: the step is HBM bound -- 12*A_pad + 12 bytes per frame are read
+// exactly once.  A warp owns 32 consecutive frames; each group of 8 lanes streams one frame
+// with 128-byte, sector-aligned float4 requests (4 frames in flight per warp-instruction),
+// accumulates the 3x3 inner-product matrix in float64 against the centre staged in shared
+// memory as float64, butterflies the 9 sums over the 8 lanes and parks them in shared memory;
+// after 8 such rounds every lane solves the QCP quartic for ONE of the warp's 32 frames, so
+// the Newton iterations run on full warps and the dist/assign update is a coalesced 128-byte
+// read-modify-write.  The shard arg-max (first occurrence) is folded into the same launch
+// through a last-block reduction that also publishes the candidate record for the next step.
+#include "eb_rmsd.cuh"
+
+namespace eb {
+
+thread_local char g_err[512] = "";
+
+int sm_count()
+{
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            return 148;
+        cached = n > 0 ? n : 148;
+    }
+    return cached;
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: one warp per frame.  The AoS frame (12*A bytes, contiguous) is pulled into shared
+// memory with coalesced loads, the centroid is accumulated in float64, and the centred
+// float32 rows x|y|z are written out with coalesced stores; trace from the ROUNDED values.
+// ------------------------------------------------------------------------------------------
+constexpr int kCtrWarps = 8;
+
+__global__ void __launch_bounds__(kCtrWarps * 32)
+k_center_and_trace(const float *__restrict__ aos, long n, int A, int A_pad, int precentered,
+                   float *__restrict__ soa, double *__restrict__ traces)
+{
+    extern __shared__ float sh_frames[];  // kCtrWarps * 3*A floats
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *buf = sh_frames + (size_t)warp * 3 * A;
+    const long warps_total = (long)gridDim.x * kCtrWarps;
+    for (long f = (long)blockIdx.x * kCtrWarps + warp; f < n; f += warps_total) {
+        const float *src = aos + (size_t)f * 3 * A;
+        for (int t = lane; t < 3 * A; t += 32) buf[t] = __ldg(src + t);
+        __syncwarp();
+        double sx = 0, sy = 0, sz = 0;
+        for (int a = lane; a < A; a += 32) {
+            sx += (double)buf[3 * a];
+            sy += (double)buf[3 * a + 1];
+            sz += (double)buf[3 * a + 2];
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            sx += shfl_xor_d(sx, m);
+            sy += shfl_xor_d(sy, m);
+            sz += shfl_xor_d(sz, m);
+        }
+        const double mx = precentered ? 0.0 : sx / A;
+        const double my = precentered ? 0.0 : sy / A;
+        const double mz = precentered ? 0.0 : sz / A;
+        float *ox = soa + (size_t)f * 3 * A_pad;
+        float *oy = ox + A_pad, *oz = oy + A_pad;
+        double g = 0;
+        for (int a = lane; a < A_pad; a += 32) {
+            float x = 0.f, y = 0.f, z = 0.f;
+            if (a < A) {
+                x = (float)((double)buf[3 * a] - mx);
+                y = (float)((double)buf[3 * a + 1] - my);
+                z = (float)((double)buf[3 * a + 2] - mz);
+                g += (double)x * x + (double)y * y + (double)z * z;
+            }
+            ox[a] = x;
+            oy[a] = y;
+            oz[a] = z;
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) g += shfl_xor_d(g, m);
+        if (lane == 0) traces[f] = g;
+        __syncwarp();
+    }
+}
+
+__global__ void k_soa_to_aos(const float *__restrict__ soa, long n, int A, int A_pad,
+                             float *__restrict__ aos)
+{
+    const long total = n * (long)A * 3;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long)gridDim.x * blockDim.x) {
+        const long f = t / (3L * A);
+        const int r = (int)(t - f * 3L * A);
+        const int a = r / 3, c = r - 3 * a;
+        aos[t] = soa[(size_t)f * 3 * A_pad + (size_t)c * A_pad + a];
+    }
+}
+
+__global__ void k_gather_frames(const float *__restrict__ soa, const double *__restrict__ traces,
+                                int A_pad, const int64_t *__restrict__ idx, long m,
+                                float *__restrict__ out, double *__restrict__ out_tr)
+{
+    const int row = 3 * A_pad / 4;  // float4 per frame
+    for (long j = blockIdx.x; j < m; j += gridDim.x) {
+        const long f = idx[j];
+        const float4 *s = reinterpret_cast<const float4 *>(soa + (size_t)f * 3 * A_pad);
+        float4 *d = reinterpret_cast<float4 *>(out + (size_t)j * 3 * A_pad);
+        for (int t = threadIdx.x; t < row; t += blockDim.x) d[t] = s[t];
+        if (threadIdx.x == 0 && out_tr) out_tr[j] = traces[f];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1
+// ------------------------------------------------------------------------------------------
+constexpr int kStepThreads = 256;
+constexpr int kStepWarps = kStepThreads / 32;
+constexpr int kSumStride = 9;  // doubles per frame slot; odd -> conflict-free 64-bit reads
+
+enum StepMode { kModeStep = 0, kModeSeed = 1, kModeDistOnly = 2 };
+
+struct StepSmem {
+    Partial red[32];
+    int flag;
+    int winner;
+    double center_trace;
+    double maxdist;
+    int64_t center_index;
+};
+
+template <bool EXACT, int MODE>
+__global__ void __launch_bounds__(kStepThreads, 2)
+k_kcenters_step_rmsd(const float *__restrict__ xyz, const double *__restrict__ traces, long n,
+                     int A, int A_pad, long frame_offset, const unsigned char *cand_in,
+                     int n_cand, size_t rec_bytes, float *dist, int *assign,
+                     int n_clusters_limit, double cutoff, eb_kc_state *state,
+                     int64_t *center_list, Partial *partials, unsigned char *cand_out,
+                     const float *center_direct, double center_trace_direct, float *out_only)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    StepSmem *ss = reinterpret_cast<StepSmem *>(smem_raw);
+    double *sums = reinterpret_cast<double *>(smem_raw + align16(sizeof(StepSmem)));
+    double *center_base = sums + kStepWarps * 32 * kSumStride;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 3, l8 = lane & 7;
+    const int A4 = A_pad >> 2;
+
+    int k = 0;
+    double Gb = 0.0;
+    CenterSmem cs = center_smem_carve(center_base, A4);
+
+    if (MODE == kModeStep) {
+        // ---- prologue: winner among the gathered candidates, stop rule -------------------
+        double cd;
+        int64_t ci;
+        const int r = pick_candidate(cand_in, n_cand, rec_bytes, cd, ci);
+        const bool active = (r >= 0) && step_active(state, n_clusters_limit, cd, cutoff, k);
+        if (!active) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                if (!state->done) {
+                    state->done = 1;
+                    state->maxdist = cd;
+                } else {
+                    state->n_noop += 1;
+                }
+            }
+            return;
+        }
+        const unsigned char *rec = cand_in + (size_t)r * rec_bytes;
+        Gb = __ldcg(&reinterpret_cast<const RecHeader *>(rec)->trace);
+        center_smem_fill(cs, reinterpret_cast<const float *>(rec + sizeof(RecHeader)), A_pad);
+        if (threadIdx.x == 0) {
+            ss->center_index = ci;
+            ss->maxdist = cd;
+        }
+        __syncthreads();
+    } else if (MODE == kModeDistOnly) {
+        Gb = center_trace_direct;
+        center_smem_fill(cs, center_direct, A_pad);
+        __syncthreads();
+    }
+
+    // ---- body -----------------------------------------------------------------------------
+    double best_d = -2.0;
+    int64_t best_i = INT64_MAX;
+    const long n_chunks = (n + 31) >> 5;
+    const long warps_total = (long)gridDim.x * kStepWarps;
+    double *my_sums = sums + (size_t)warp * 32 * kSumStride;
+
+    for (long chunk = (long)blockIdx.x * kStepWarps + warp; chunk < n_chunks;
+         chunk += warps_total) {
+        const long base = chunk << 5;
+        if (MODE != kModeSeed) {
+#pragma unroll 1
+            for (int s = 0; s < 8; ++s) {
+                const long f = base + 4 * s + g;
+                double m[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                if (f < n)
+                    frame_inner_products<EXACT>(m, xyz + (size_t)f * 3 * A_pad, A4, l8, cs);
+                group8_reduce(m);
+                if (l8 == 0) {
+                    double *dst = my_sums + (4 * s + g) * kSumStride;
+#pragma unroll
+                    for (int e = 0; e < 9; ++e) dst[e] = m[e];
+                }
+            }
+            __syncwarp();
+        }
+        const long f = base + lane;
+        if (f < n) {
+            double cur;
+            if (MODE == kModeSeed) {
+                cur = (double)dist[f];
+            } else {
+                double m[9];
+                const double *src = my_sums + lane * kSumStride;
+#pragma unroll
+                for (int e = 0; e < 9; ++e) m[e] = src[e];
+                const float d = rmsd_from_msd(qcp_msd(m, traces[f], Gb, A));
+                if (MODE == kModeDistOnly) {
+                    out_only[f] = d;
+                    cur = 0.0;
+                } else {
+                    const float old = dist[f];
+                    if (d < old) {  // strict '<', kcenters.py:304
+                        dist[f] = d;
+                        assign[f] = k;
+                    }
+                    cur = (double)((d < old) ? d : old);
+                }
+            }
+            if (cur > best_d) {  // frames arrive in increasing f per lane: first max kept
+                best_d = cur;
+                best_i = f;
+            }
+        }
+        if (MODE != kModeSeed) __syncwarp();
+    }
+    if (MODE == kModeDistOnly) return;
+
+    // ---- epilogue: shard arg-max, candidate record, centre list ----------------------------
+    if (!grid_argmax_last_block(best_d, best_i, partials, state, ss->red, &ss->flag)) return;
+
+    RecHeader *out = reinterpret_cast<RecHeader *>(cand_out);
+    const bool empty = (best_i == INT64_MAX);
+    if (!empty) {
+        const float4 *src = reinterpret_cast<const float4 *>(xyz + (size_t)best_i * 3 * A_pad);
+        float4 *dst = reinterpret_cast<float4 *>(cand_out + sizeof(RecHeader));
+        for (int t = threadIdx.x; t < 3 * A4; t += blockDim.x) dst[t] = __ldcg(src + t);
+    }
+    if (threadIdx.x == 0) {
+        out->dist = empty ? -1.0 : best_d;
+        out->index = empty ? -1 : frame_offset + best_i;
+        out->trace = empty ? 0.0 : traces[best_i];
+        out->reserved = 0;
+        if (MODE == kModeStep) {
+            center_list[k] = ss->center_index;
+            state->n_centers = k + 1;
+            state->last_center = ss->center_index;
+            state->maxdist = ss->maxdist;
+        } else {
+            state->n_centers = n_clusters_limit;  // seed mode: carries first_center_id
+            state->done = 0;
+            state->n_noop = 0;
+            state->maxdist = 0.0;
+            state->last_center = -1;
+        }
+        state->local_maxdist = empty ? -1.0 : best_d;
+        state->blocks_done = 0;
+        __threadfence();
+    }
+}
+
+static size_t step_smem_bytes(int A_pad)
+{
+    return align16(sizeof(StepSmem)) + sizeof(double) * kStepWarps * 32 * kSumStride +
+           sizeof(double) * 3 * (size_t)A_pad;
+}
+
+static int step_grid(long n)
+{
+    const long chunks = (n + 31) / 32;
+    long blocks = (chunks + kStepWarps - 1) / kStepWarps;
+    const long cap = 2L * sm_count();
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+template <bool EXACT, int MODE>
+static int launch_step(const float *xyz, const double *traces, long n, int A, long frame_offset,
+                       const void *cand_in, int n_cand, float *dist, int *assign,
+                       int n_clusters_limit, double cutoff, eb_kc_state *state,
+                       int64_t *center_list, void *partials, void *cand_out,
+                       const float *center_direct, double center_trace_direct, float *out_only,
+                       cudaStream_t stream)
+{
+    const int A_pad = rmsd_apad(A);
+    const size_t smem = step_smem_bytes(A_pad);
+    if (smem > 227 * 1024)
+        return fail(EB_ERR_LIMIT, "%s: n_atoms=%ld needs %ld bytes of shared memory (max 232448)",
+                    "rmsd step", (long)A, (long)smem);
+    auto kern = k_kcenters_step_rmsd<EXACT, MODE>;
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+        configured = smem;
+    }
+    const size_t rec_bytes = sizeof(RecHeader) + sizeof(float) * 3 * (size_t)A_pad;
+    kern<<<step_grid(n), kStepThreads, smem, stream>>>(
+        xyz, traces, n, A, A_pad, frame_offset, (const unsigned char *)cand_in, n_cand, rec_bytes,
+        dist, assign, n_clusters_limit, cutoff, state, center_list, (Partial *)partials,
+        (unsigned char *)cand_out, center_direct, center_trace_direct, out_only);
+    EB_LAUNCH_CHECK();
+    return EB_OK;
+}
+
+}  // namespace eb
+
+using namespace eb;
+
+extern "C" {
+
+int eb_version(void) { return 100; }
+const char *eb_last_error(void) { return eb::g_err; }
+int eb_sm_count(void) { return eb::sm_count(); }
+
+int eb_rmsd_apad(int n_atoms) { return rmsd_apad(n_atoms); }
+size_t eb_rmsd_record_bytes(int n_atoms)
+{
+    return sizeof(RecHeader) + sizeof(float) * 3 * (size_t)rmsd_apad(n_atoms);
+}
+size_t eb_kc_partials_bytes(void) { return sizeof(Partial) * kMaxGrid; }
+
+int eb_center_and_trace(const float *xyz_aos, int64_t n, int n_atoms, int precentered,
+                        float *xyz_soa, double *traces, void *stream)
+{
+    EB_CHECK_ARG(n >= 0 && n_atoms > 0, "center_and_trace: need n >= 0 and n_atoms > 0");
+    if (n == 0) return EB_OK;
+    EB_CHECK_ARG(xyz_aos && xyz_soa && traces, "center_and_trace: null pointer");
+    const size_t smem = sizeof(float) * kCtrWarps * 3 * (size_t)n_atoms;
+    if (smem > 227 * 1024)
+        return fail(EB_ERR_LIMIT, "%s: n_atoms=%ld too large for the centring kernel",
+                    "center_and_trace", (long)n_atoms);
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        EB_CUDA(cudaFuncSetAttribute(k_center_and_trace,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    long blocks = (n + kCtrWarps - 1) / kCtrWarps;
+    const long cap = 8L * sm_count();
+    if (blocks > cap) blocks = cap;
+    k_center_and_trace<<<(int)blocks, kCtrWarps * 32, smem, (cudaStream_t)stream>>>(
+        xyz_aos, n, n_atoms, rmsd_apad(n_atoms), precentered, xyz_soa, traces);
+    EB_LAUNCH_CHECK();
+    return EB_OK;
+}
+
+int eb_soa_to_aos(const float *xyz_soa, int64_t n, int n_atoms, float *xyz_aos, void *stream)
+{
+    EB_CHECK_ARG(n >= 0 && n_atoms > 0, "soa_to_aos: bad shape");
+    if (n == 0) return EB_OK;
+    long total = n * (long)n_atoms * 3;
+    long blocks = (total + 255) / 256;
+    if (blocks > 16L * sm_count()) blocks = 16L * sm_count();
+    k_soa_to_aos<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(xyz_soa, n, n_atoms,
+                                                                rmsd_apad(n_atoms), xyz_aos);
+    EB_LAUNCH_CHECK();
+    return EB_OK;
+}
+
+int eb_gather_frames(const float *xyz_soa, const double *traces, int n_atoms, const int64_t *idx,
+                     int64_t m, float *out_soa, double *out_traces, void *stream)
+{
+    EB_CHECK_ARG(m >= 0 && n_atoms > 0, "gather_frames: bad shape");
+    if (m == 0) return EB_OK;
+    long blocks = m < 4L * sm_count() ? m : 4L * sm_count();
+    k_gather_frames<<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(
+        xyz_soa, traces, rmsd_apad(n_atoms), idx, m, out_soa, out_traces);
+    EB_LAUNCH_CHECK();
+    return EB_OK;
+}
+
+int eb_kcenters_step_rmsd(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
+                          int64_t frame_offset, const void *cand_in, int n_cand, float *dist,
+                          int32_t *assign, int32_t n_clusters_limit, double dist_cutoff,
+                          eb_kc_state *state, int64_t *center_list, void *partials,
+                          void *cand_out, int exact, void *stream)
+{
+    EB_CHECK_ARG(n >= 0 && n_atoms > 0, "kcenters_step_rmsd: bad shape");
+    EB_CHECK_ARG(n_cand >= 1 && cand_in && cand_out && state && partials && center_list,
+                 "kcenters_step_rmsd: null pointer / n_cand < 1");
+    EB_CHECK_ARG(n < (int64_t(1) << 40), "kcenters_step_rmsd: shard too large");
+    if (exact)
+        return launch_step<true, kModeStep>(xyz_soa, traces, n, n_atoms, frame_offset, cand_in,
+                                            n_cand, dist, assign, n_clusters_limit, dist_cutoff,
+                                            state, center_list, partials, cand_out, nullptr, 0.0,
+                                            nullptr, (cudaStream_t)stream);
+    return launch_step<false, kModeStep>(xyz_soa, traces, n, n_atoms, frame_offset, cand_in,
+                                         n_cand, dist, assign, n_clusters_limit, dist_cutoff,
+                                         state, center_list, partials, cand_out, nullptr, 0.0,
+                                         nullptr, (cudaStream_t)stream);
+}
+
+int eb_kcenters_seed_rmsd(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
+                          int64_t frame_offset, const float *dist, int32_t first_center_id,
+                          eb_kc_state *state, void *partials, void *cand_out, void *stream)
+{
+    EB_CHECK_ARG(n >= 0 && n_atoms > 0, "kcenters_seed_rmsd: bad shape");
+    EB_CHECK_ARG(state && partials && cand_out, "kcenters_seed_rmsd: null pointer");
+    EB_CUDA(cudaMemsetAsync(state, 0, sizeof(eb_kc_state), (cudaStream_t)stream));
+    return launch_step<true, kModeSeed>(xyz_soa, traces, n, n_atoms, frame_offset, nullptr, 0,
+                                        const_cast<float *>(dist), nullptr, first_center_id, 0.0,
+                                        state,
+                                        nullptr, partials, cand_out, nullptr, 0.0, nullptr,
+                                        (cudaStream_t)stream);
+}
+
+int eb_rmsd_one_to_all(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
+                       const float *center_soa, double center_trace, float *out, int exact,
+                       void *stream)
+{
+    EB_CHECK_ARG(n >= 0 && n_atoms > 0, "rmsd_one_to_all: bad shape");
+    if (n == 0) return EB_OK;
+    EB_CHECK_ARG(xyz_soa && traces && center_soa && out, "rmsd_one_to_all: null pointer");
+    if (exact)
+        return launch_step<true, kModeDistOnly>(xyz_soa, traces, n, n_atoms, 0, nullptr, 0,
+                                                nullptr, nullptr, 0, 0.0, nullptr, nullptr,
+                                                nullptr, nullptr, center_soa, center_trace, out,
+                                                (cudaStream_t)stream);
+    return launch_step<false, kModeDistOnly>(xyz_soa, traces, n, n_atoms, 0, nullptr, 0, nullptr,
+                                             nullptr, 0, 0.0, nullptr, nullptr, nullptr, nullptr,
+                                             center_soa, center_trace, out,
+                                             (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,192 @@
+/*
+ * enspara_b200.h -- C ABI of the B200-native clustering hot path (libenspara_b200.so).
+ *
+ * This is the drop-in boundary for enspara's conformational-clustering path.  The reference
+ * is Python that reaches native code through two FFI seams; each entry point below names the
+ * reference interface it replaces (paths under /root/reference/enspara/):
+ *
+ *   seam 1  mdtraj.rmsd (C/SSE, third party)           cluster/util.py:290-291, apps/cluster.py:210
+ *   seam 2  geometry/libdist.pyx (Cython/OpenMP)        libdist.pyx:100-183
+ *   plus the numpy bookkeeping wrapped around them      cluster/kcenters.py:282-309,
+ *                                                       cluster/util.py:186-203,
+ *                                                       cluster/kmedoids.py:611-694
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*), never
+ *     allocates device memory and never synchronises, unless stated;
+ *   - return value 0 = ok; non-zero = error, text via eb_last_error() (thread local);
+ *     EB_ERR_INVALID maps to enspara.exception.DataInvalid in the Python host layer;
+ *   - frames of a trajectory live as float32 "SoA blocks": frame f occupies 3*A_pad floats,
+ *     x[0..A_pad) y[0..A_pad) z[0..A_pad), A_pad = eb_rmsd_apad(A) (multiple of 8 so every
+ *     row starts on a 32-byte sector), padding atoms are 0; coordinates are pre-centred and
+ *     traces[f] = sum |x|^2 (float64) is stored beside them.
+ *   - a "candidate record" is how one shard publishes its farthest frame after a step:
+ *       [ 0] double  dist      current max of min-distances on the shard (-1 if shard empty)
+ *       [ 8] int64   index     GLOBAL frame index of that frame (lowest index among ties)
+ *       [16] double  trace     RMSD: trace of that frame; else 0
+ *       [24] int64   reserved
+ *       [32] payload           RMSD: 3*A_pad float32 SoA coords; euclid: F elements of dtype
+ *     Records are what ranks exchange (one NCCL all-gather per k-centers iteration); the next
+ *     step picks the winner among the gathered records on the device, so the host never needs
+ *     to know which rank owns the new centre.
+ */
+#ifndef ENSPARA_B200_H
+#define ENSPARA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EB_OK 0
+#define EB_ERR_INVALID 1 /* bad shapes / arguments  -> DataInvalid            */
+#define EB_ERR_CUDA 2    /* CUDA runtime error      -> RuntimeError           */
+#define EB_ERR_LIMIT 3   /* size beyond a documented limit -> RuntimeError    */
+
+/* element types accepted by the libdist replacements (libdist.pyx:9-15 FLOAT_TYPE_T) */
+#define EB_DT_F32 0
+#define EB_DT_F64 1
+#define EB_DT_I8 2
+#define EB_DT_I16 3
+#define EB_DT_I32 4
+#define EB_DT_I64 5
+
+/* metrics of the fused feature-vector kernels (cluster/util.py:289-313) */
+#define EB_METRIC_EUCLIDEAN 0
+#define EB_METRIC_MANHATTAN 1
+#define EB_METRIC_SQEUCLIDEAN 2 /* the squared-euclid callable of test_cluster.py:509-510 */
+
+/* k-centers device state, one per shard; read back by the host once per batch of steps */
+typedef struct eb_kc_state {
+    int32_t n_centers;    /* centres chosen so far                                        */
+    int32_t done;         /* 1 once the stop rule of kcenters.py:217 fired                */
+    uint32_t blocks_done; /* internal: last-block ticket                                  */
+    int32_t n_noop;       /* steps that were skipped because done==1 (diagnostic)         */
+    double maxdist;       /* GLOBAL max of min-distances seen by the last step's prologue */
+    double local_maxdist; /* max of min-distances on this shard after the last step       */
+    int64_t last_center;  /* global index of the last centre chosen                       */
+    int64_t reserved[3];
+} eb_kc_state; /* 64 bytes */
+
+int eb_version(void);
+const char *eb_last_error(void);
+/* number of SMs of the current device (grid sizing is done inside the library) */
+int eb_sm_count(void);
+
+/* ---- layout helpers ------------------------------------------------------------------- */
+int eb_rmsd_apad(int n_atoms);
+size_t eb_rmsd_record_bytes(int n_atoms);
+/* bytes of scratch ("partials") the step / seed kernels need; constant per device */
+size_t eb_kc_partials_bytes(void);
+
+/* ---- K5: centring + trace, AoS -> SoA --------------------------------------------------
+ * Replaces the per-call copy + inplace_center_and_trace_atom_major of mdtraj.rmsd (done once
+ * here instead of once per distance call).  xyz_aos is (n, n_atoms, 3) float32 C-order as in
+ * md.Trajectory.xyz.  precentered != 0 skips the centroid subtraction (cluster/util.py:625-629
+ * `precentered=True`).  */
+int eb_center_and_trace(const float *xyz_aos, int64_t n, int n_atoms, int precentered,
+                        float *xyz_soa, double *traces, void *stream);
+/* inverse layout change for handing centres back to the host as (n, n_atoms, 3) */
+int eb_soa_to_aos(const float *xyz_soa, int64_t n, int n_atoms, float *xyz_aos, void *stream);
+/* gather frames idx[0..m) (local indices) of an SoA block into a dense SoA block + traces */
+int eb_gather_frames(const float *xyz_soa, const double *traces, int n_atoms,
+                     const int64_t *idx, int64_t m, float *out_soa, double *out_traces,
+                     void *stream);
+
+/* ---- K1: fused k-centers step, RMSD -----------------------------------------------------
+ * One launch == one iteration of kcenters.py:243-311 (and :314-378 for a shard):
+ *   prologue  pick the winner among n_cand candidate records (max dist, lowest global index)
+ *             -> new centre; apply the stop rule of kcenters.py:217
+ *             (n_centers < n_clusters_limit && maxdist > dist_cutoff), else set state->done;
+ *   body      stream every frame once, 3x3 inner-product matrix in float64, Theobald QCP,
+ *             float32 RMSD, strict '<' update of dist/assign (kcenters.py:304-306);
+ *   epilogue  shard arg-max (first occurrence) -> cand_out record, centre list append.
+ * cand_in may alias cand_out (single GPU).  dist is float32 (values are float32 in the
+ * reference too: md.rmsd returns float32), assign int32; the host layer widens them to the
+ * reference's float64 / int64 when it copies results out.  exact=1 accumulates the matrix in
+ * float64 (parity mode, default); exact=0 uses float32 blocks of 8 atoms + float64 block sums. */
+int eb_kcenters_step_rmsd(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
+                          int64_t frame_offset, const void *cand_in, int n_cand,
+                          float *dist, int32_t *assign, int32_t n_clusters_limit,
+                          double dist_cutoff, eb_kc_state *state, int64_t *center_list,
+                          void *partials, void *cand_out, int exact, void *stream);
+/* seed: arg-max of the CURRENT dist array -> cand_out (all +inf gives frame 0, which is the
+ * reference's first centre, kcenters.py:199,282,326-328); resets *state with
+ * n_centers = first_center_id (> 0 when continuing from init_centers, kcenters.py:200-206). */
+int eb_kcenters_seed_rmsd(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
+                          int64_t frame_offset, const float *dist, int32_t first_center_id,
+                          eb_kc_state *state, void *partials, void *cand_out, void *stream);
+/* one-vs-all RMSD only (the md.rmsd(traj, frame) call itself, util.py:290): out float32[n] */
+int eb_rmsd_one_to_all(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
+                       const float *center_soa, double center_trace, float *out, int exact,
+                       void *stream);
+
+#ifdef EB_PLANNED /* declared ahead of their implementation; not exported yet */
+size_t eb_feat_record_bytes(int64_t n_features, int dtype);
+/* ---- K2: fused k-centers step, feature vectors (libdist.pyx:100-145) -------------------
+ * X is (n, F) row-major of `dtype`; dist is float64 like libdist's output; arithmetic follows
+ * the generated C of the reference bit for bit: typed difference, typed square, float64
+ * accumulation in j order, double sqrt. */
+int eb_kcenters_step_feat(const void *X, int64_t n, int64_t n_features, int dtype, int metric,
+                          int64_t frame_offset, const void *cand_in, int n_cand, double *dist,
+                          int32_t *assign, int32_t n_clusters_limit, double dist_cutoff,
+                          eb_kc_state *state, int64_t *center_list, void *partials,
+                          void *cand_out, void *stream);
+int eb_kcenters_seed_feat(const void *X, int64_t n, int64_t n_features, int dtype,
+                          int64_t frame_offset, const double *dist, int32_t first_center_id,
+                          eb_kc_state *state, void *partials, void *cand_out, void *stream);
+/* libdist.euclidean / manhattan(X, y) itself: out float64[n] */
+int eb_feat_one_to_all(const void *X, int64_t n, int64_t n_features, int dtype, int metric,
+                       const void *y, double *out, void *stream);
+
+/* ---- K3: many-centres nearest-centre assignment (cluster/util.py:159-205) ---------------
+ * For every frame the nearest of k centres, strict '<' in centre order (lowest centre index
+ * wins ties), starting from dist/assign as given when `accumulate` != 0, else from +inf / 0.
+ * frame_idx (optional, may be NULL) restricts the pass to a subset of local frames -- the
+ * X[dst_up_assig_this] re-assignment of kmedoids.py:666-667.  Results are written at the
+ * subset positions of out_dist/out_assign (dense when frame_idx is NULL). */
+int eb_rmsd_assign(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
+                   const float *centers_soa, const double *center_traces, int32_t k,
+                   const int64_t *frame_idx, int64_t n_idx, float *out_dist,
+                   int32_t *out_assign, int accumulate, void *stream);
+int eb_feat_assign(const void *X, int64_t n, int64_t n_features, int dtype, int metric,
+                   const void *centers, int32_t k, const int64_t *frame_idx, int64_t n_idx,
+                   double *out_dist, int32_t *out_assign, int accumulate, void *stream);
+
+/* ---- K4/K6: PAM bookkeeping (cluster/kmedoids.py:611-694) -------------------------------
+ * eb_pam_classify: given the full-pass distances to the proposal (new_ctr_dist) builds
+ *   new_dist/new_assign for the 'dn' and 'up_other' cases, compacts the 'up_this' frame
+ *   indices (ascending) into ambig_idx and counts them in *n_ambig.
+ * eb_pam_cost:     sum(dist^2) in float64, deterministic order (kmedoids.py:478-479 numerator).
+ * eb_count_members / eb_select_member: |{i: assign[i]==cid}| and the kth such i (ascending),
+ *   i.e. np.where(assignments == cid)[0][kth] of kmedoids.py:611 + :514.
+ * DT = 0 for float32 distance arrays (RMSD), 1 for float64 (feature metrics). */
+int eb_pam_classify(const void *new_ctr_dist, const void *dist, const int32_t *assign, int64_t n,
+                    int dist_is_f64, int32_t cid, void *new_dist, int32_t *new_assign,
+                    int64_t *ambig_idx, int64_t *n_ambig, void *scratch, void *stream);
+size_t eb_pam_scratch_bytes(int64_t n);
+int eb_sum_squares(const void *dist, int64_t n, int dist_is_f64, double *out, void *scratch,
+                   void *stream);
+int eb_count_members(const int32_t *assign, int64_t n, int32_t k, int64_t *counts, void *stream);
+int eb_select_member(const int32_t *assign, int64_t n, int32_t cid, int64_t kth, int64_t *out,
+                     void *scratch, void *stream);
+
+/* ---- synthetic data: counter-based generator keyed on (seed, global frame) -
+ * Writes centred SoA frames + traces directly in HBM so a 10M x 500-atom trajectory never has
+ * to exist on the host.  The same generator is restated in numpy (enspara_b200/synth.py) for
+ * down-scaled oracle comparisons; eb_synth_trajectory_aos writes the raw (n,A,3) frames. */
+int eb_synth_trajectory_aos(float *xyz_aos, int64_t n, int n_atoms, int64_t first_frame,
+                            uint64_t seed, const float *base_conformers, int n_base,
+                            void *stream);
+int eb_synth_features(float *X, int64_t n, int64_t n_features, int64_t first_row, uint64_t seed,
+                      void *stream);
+
+#endif /* EB_PLANNED */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ENSPARA_B200_H */

@@ -1,0 +1,213 @@
+"""GPU parity: fused RMSD k-centers path (K5 + K1) against the oracle.
+
+Tolerances (BASELINE.json north_star): centre indices and assignments identical to the oracle
+except at near-ties below 1e-6 nm; distances within 1e-5 relative.  The CUDA path accumulates
+the inner-product matrix in float64 like the oracle's "truth" variant, so in practice the
+float32 results are bit-identical for almost every frame; the tests assert the stated
+tolerance and report the bitwise mismatch fraction.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5      # north_star: distances match to 1e-5 relative
+ATOL = 1e-6      # nm; near-tie threshold of the north_star
+
+
+@pytest.fixture(scope="module")
+def cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from enspara_b200 import _lib
+    _lib.load()
+    return torch
+
+
+def _assert_lockstep(ref_trace, got_centers, d_oracle_fn):
+    """Centre sequences must agree; a divergence is only tolerated at a documented near-tie."""
+    for i, ((c_ref, _), c_got) in enumerate(zip(ref_trace, got_centers)):
+        if c_ref != c_got:
+            gap = abs(d_oracle_fn(i, c_ref) - d_oracle_fn(i, c_got))
+            assert gap < ATOL, "centre %d differs (%d vs %d) and is not a near-tie (gap %g)" % (
+                i, c_ref, c_got, gap)
+            pytest.xfail("near-tie below 1e-6 nm at centre %d; sequences legitimately diverge" % i)
+
+
+def test_center_and_trace_matches_oracle(cuda):
+    from enspara_b200 import synth
+    from enspara_b200.device import DeviceTrajectory
+    from oracle import distances as od
+    for A in (22, 264, 500, 7):
+        X = synth.trajectory(257, A, seed=3)
+        dev = DeviceTrajectory.from_host(X)
+        got = dev.to_host_aos()
+        ref, t64, _ = od.center_and_trace(X)
+        assert dev.a_pad % 8 == 0 and dev.a_pad >= A
+        # centred coordinates: float32 rounding of (x - mean); the mean is summed in a different
+        # order on the GPU, which can move a coordinate by at most one ulp, extremely rarely
+        assert np.mean(got != ref) < 1e-4
+        np.testing.assert_allclose(got, ref, rtol=0, atol=1e-6)
+        np.testing.assert_allclose(dev.traces.cpu().numpy(), t64, rtol=1e-12)
+        # padding atoms are zero
+        pad = dev.xyz[:, :, A:].cpu().numpy()
+        assert not pad.any()
+
+
+@pytest.mark.parametrize("A,n", [(22, 501), (264, 3000), (500, 2000), (13, 100)])
+def test_one_to_all_rmsd_matches_oracle(cuda, A, n):
+    from enspara_b200 import synth
+    from enspara_b200.cluster import util
+    from oracle import distances as od
+    X = synth.trajectory(n, A, seed=11)
+    T = od.Trajectory(X)
+    for c in (0, n // 2, n - 1):
+        want = od.rmsd(T, T[c])
+        got = util.RMSD(T, T[c])
+        assert got.dtype == np.float32 and got.shape == (n,)
+        np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL)
+        assert np.mean(got != want) < 0.02, "more than 2%% of float32 results differ bitwise"
+
+
+def test_one_to_all_fast_mode_within_tolerance(cuda):
+    from enspara_b200 import synth
+    from enspara_b200.cluster import _ops, util
+    from enspara_b200.device import DeviceTrajectory
+    from oracle import distances as od
+    X = synth.trajectory(2000, 264, seed=5)
+    T = od.Trajectory(X)
+    data = DeviceTrajectory.from_host(X)
+    want = od.rmsd(T, T[7])
+    got = _ops.one_to_all_device(util.RMSD, data, data.gather([7]), exact=False).cpu().numpy()
+    sel = want > 0.05
+    np.testing.assert_allclose(got[sel], want[sel], rtol=1e-4)
+
+
+def test_kcenters_frame0_golden(cuda, frame0_xyz, golden):
+    """The reference's own RMSD goldens (enspara/test/test_cluster.py:200-238)."""
+    from enspara_b200.cluster import kcenters
+    from oracle import distances as od
+    T = od.Trajectory(frame0_xyz)
+
+    r = kcenters.kcenters(T, "rmsd", dist_cutoff=0.1)
+    assert len(np.unique(r.assignments)) == 17
+    assert abs(np.average(r.distances) - 0.074690734158752686) < 0.5e-5
+    assert abs(np.std(r.distances) - 0.018754008455304401) < 0.5e-5
+    assert r.distances.max() < 0.1
+    assert r.assignments.dtype == np.int64 and r.distances.dtype == np.float64
+    assert [int(c) for c in r.center_indices] == golden["frame0_cut01_centers"].tolist()
+    np.testing.assert_array_equal(r.assignments, golden["frame0_cut01_assign"])
+    np.testing.assert_allclose(r.distances, golden["frame0_cut01_dist"], rtol=RTOL, atol=ATOL)
+    assert len(r.centers) == 17 and r.centers[1].xyz.shape == (1, 22, 3)
+
+    r = kcenters.kcenters(T, "rmsd", n_clusters=3)
+    assert len(np.unique(r.assignments)) == 3
+    assert abs(np.average(r.distances) - 0.10387578309920734) < 0.5e-7
+    assert abs(np.std(r.distances) - 0.018355072790569946) < 0.5e-7
+    assert [int(c) for c in r.center_indices] == golden["frame0_k3_centers"].tolist()
+    np.testing.assert_array_equal(r.assignments, golden["frame0_k3_assign"])
+
+
+def test_kcenters_object_frame0(cuda, frame0_xyz):
+    """enspara/test/test_cluster.py:29-73."""
+    from enspara_b200.cluster import KCenters
+    from enspara_b200.exception import ImproperlyConfigured
+    from oracle import distances as od
+    T = od.Trajectory(frame0_xyz)
+    with pytest.raises(ImproperlyConfigured):
+        KCenters(metric="rmsd")
+    c = KCenters(metric="rmsd", n_clusters=5).fit(T)
+    assert len(np.unique(c.labels_)) == 5
+    c = KCenters(metric="rmsd", cluster_radius=0.1).fit(T)
+    assert c.distances_.max() < 0.1
+    c = KCenters(metric="rmsd", n_clusters=5, cluster_radius=0.1).fit(T)
+    assert len(np.unique(c.labels_)) == 5
+    assert c.runtime_ > 0
+
+
+def test_kcenters_synthetic_c1_matches_oracle(cuda):
+    """BASELINE config 1 shape (264 atoms), reduced to 4000 frames so the oracle takes seconds."""
+    from enspara_b200 import synth
+    from enspara_b200.cluster import kcenters
+    from oracle import cluster as oc
+    from oracle import distances as od
+    X = synth.trajectory(4000, 264, seed=1)
+    T = od.Trajectory(X)
+    trace = []
+    ref = oc.kcenters(T, od.rmsd, n_clusters=40, trace=trace)
+    got = kcenters.kcenters(T, "rmsd", n_clusters=40)
+    got_c = [int(c) for c in got.center_indices]
+
+    def d_oracle(i, c):
+        # distance of frame c to its nearest of the first i centres, per the oracle
+        a, d = oc.assign_to_nearest_center(T[[c]], [T[j] for j in ref.center_indices[:i]],
+                                           od.rmsd) if i else (None, [np.inf])
+        return d[0]
+    _assert_lockstep(trace, got_c, d_oracle)
+    assert got_c == [int(c) for c in ref.center_indices]
+    np.testing.assert_allclose(got.distances, ref.distances, rtol=RTOL, atol=ATOL)
+    mism = got.assignments != ref.assignments
+    if mism.any():  # only allowed where the two nearest centres are a near-tie
+        idx = np.where(mism)[0]
+        for f in idx:
+            d_all = np.array([od.rmsd(T[[f]], T[c])[0] for c in ref.center_indices])
+            top2 = np.sort(d_all)[:2]
+            assert top2[1] - top2[0] < ATOL
+    assert mism.mean() < 1e-3
+
+
+def test_kcenters_cutoff_and_limit_interplay(cuda):
+    from enspara_b200 import synth
+    from enspara_b200.cluster import kcenters
+    from oracle import cluster as oc
+    from oracle import distances as od
+    X = synth.trajectory(1500, 50, seed=2)
+    T = od.Trajectory(X)
+    for kw in (dict(dist_cutoff=1.2), dict(dist_cutoff=0.9, n_clusters=7),
+               dict(n_clusters=1), dict(dist_cutoff=100.0)):
+        ref = oc.kcenters(T, od.rmsd, **kw)
+        got = kcenters.kcenters(T, "rmsd", **kw)
+        assert [int(c) for c in got.center_indices] == [int(c) for c in ref.center_indices], kw
+        np.testing.assert_array_equal(got.assignments, ref.assignments)
+        np.testing.assert_allclose(got.distances, ref.distances, rtol=RTOL, atol=ATOL)
+
+
+def test_kcenters_ragged_sizes(cuda):
+    """Sizes that are not multiples of the 32-frame warp chunk or the 8-atom padding."""
+    from enspara_b200 import synth
+    from enspara_b200.cluster import kcenters
+    from oracle import cluster as oc
+    from oracle import distances as od
+    for n, A in ((1, 5), (2, 9), (31, 17), (33, 8), (1025, 23)):
+        X = synth.trajectory(n, A, seed=n)
+        T = od.Trajectory(X)
+        k = min(n, 6)
+        ref = oc.kcenters(T, od.rmsd, n_clusters=k)
+        got = kcenters.kcenters(T, "rmsd", n_clusters=k)
+        assert [int(c) for c in got.center_indices] == [int(c) for c in ref.center_indices]
+        np.testing.assert_array_equal(got.assignments, ref.assignments)
+        np.testing.assert_allclose(got.distances, ref.distances, rtol=RTOL, atol=ATOL)
+
+
+def test_kcenters_full_size_properties(cuda):
+    """BASELINE config-1 full size (20k x 264, k=100): size-independent properties."""
+    from enspara_b200 import synth
+    from enspara_b200.cluster import kcenters, util
+    X = synth.trajectory(20000, 264, seed=0)
+    r = kcenters.kcenters(X, "rmsd", n_clusters=100)
+    c = [int(i) for i in r.center_indices]
+    assert len(c) == 100 and len(set(c)) == 100 and c[0] == 0
+    assert np.all(r.assignments >= 0) and r.assignments.max() == 99
+    # every centre is assigned to itself at (numerically) zero distance
+    assert np.all(r.distances[c] < 1e-4)
+    np.testing.assert_array_equal(r.assignments[c], np.arange(100))
+    # idempotence: re-assigning against the chosen centres reproduces the result
+    a2, d2 = util.assign_to_nearest_center(X, X[c], "rmsd")
+    np.testing.assert_array_equal(a2, r.assignments)
+    np.testing.assert_array_equal(d2, r.distances)
+    # the k-centers radius sequence is non-increasing: distance of centre i to the earlier
+    # centres at the time it was picked equals the max of min-distances then
+    # (checked through the final distances: nobody is farther than the last radius)
+    last_radius = util.RMSD(X[c[:-1]], X[c[-1]]).min()
+    assert r.distances.max() <= last_radius + 1e-6
