@@ -45,17 +45,17 @@ SIGNATURES = {
                                      _dbl, _vp, _vp, _vp, _vp, _int, _vp]),
     "eb_kcenters_seed_rmsd": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _i32, _vp, _vp, _vp,
                                      _vp]),
-    "eb_rmsd_one_to_all": (_int, [_vp, _vp, _i64, _int, _vp, _dbl, _vp, _int, _vp]),
+    "eb_rmsd_one_to_all": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _vp, _int, _vp]),
     "eb_kcenters_step_feat": (_int, [_vp, _i64, _i64, _int, _int, _i64, _vp, _int, _vp, _vp,
                                      _i32, _dbl, _vp, _vp, _vp, _vp, _vp]),
     "eb_kcenters_seed_feat": (_int, [_vp, _i64, _i64, _int, _i64, _vp, _i32, _vp, _vp, _vp,
                                      _vp]),
     "eb_feat_one_to_all": (_int, [_vp, _i64, _i64, _int, _int, _vp, _vp, _vp]),
     "eb_rmsd_assign": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _int,
-                              _vp]),
-    "eb_feat_assign": (_int, [_vp, _i64, _i64, _int, _int, _vp, _i32, _vp, _i64, _vp, _vp,
                               _int, _vp]),
-    "eb_pam_classify": (_int, [_vp, _vp, _vp, _i64, _int, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "eb_feat_assign": (_int, [_vp, _i64, _i64, _int, _int, _vp, _i32, _vp, _i64, _vp, _vp,
+                              _int, _int, _vp]),
+    "eb_pam_classify": (_int, [_vp, _vp, _vp, _i64, _int, _i32, _vp, _vp, _vp, _vp, _vp]),
     "eb_pam_scratch_bytes": (_sz, [_i64]),
     "eb_sum_squares": (_int, [_vp, _i64, _int, _vp, _vp, _vp]),
     "eb_count_members": (_int, [_vp, _i64, _i32, _vp, _vp]),
@@ -66,9 +66,6 @@ SIGNATURES = {
 
 #: declared under ``#ifdef EB_PLANNED`` in the header; not yet exported by the library
 PLANNED = {
-    "eb_feat_record_bytes", "eb_kcenters_step_feat", "eb_kcenters_seed_feat",
-    "eb_feat_one_to_all", "eb_rmsd_assign", "eb_feat_assign", "eb_pam_classify",
-    "eb_pam_scratch_bytes", "eb_sum_squares", "eb_count_members", "eb_select_member",
     "eb_synth_trajectory_aos", "eb_synth_features",
 }
 

@@ -38,26 +38,22 @@ def _single_frame_soa(metric, y, like):
     return DeviceFeatures.from_host(arr[None])
 
 
-def one_to_all_device(metric, data, center, exact=True):
-    """Distances of every frame of ``data`` to ``center`` as a device tensor
-    (float32 for RMSD like md.rmsd, float64 for libdist metrics)."""
+def one_to_all_device(metric, data, center, exact=True, out=None, **_unused):
+    """Distances of every frame of ``data`` to the single frame ``center`` as a device tensor
+    (float32 for RMSD like md.rmsd, float64 for libdist metrics).  No host synchronisation."""
     n = len(data)
     if metric.is_rmsd:
-        out = torch.empty(n, dtype=torch.float32, device=data.xyz.device)
+        if out is None:
+            out = torch.empty(n, dtype=torch.float32, device=data.xyz.device)
         _lib.call("eb_rmsd_one_to_all", ptr(data.xyz), ptr(data.traces), n, data.n_atoms,
-                  ptr(center.xyz), _trace0(center),
-                  ptr(out), int(exact), stream_ptr())
+                  ptr(center.xyz), ptr(center.traces), ptr(out), int(exact), stream_ptr())
         return out
-    out = torch.empty(n, dtype=torch.float64, device=data.X.device)
+    if out is None:
+        out = torch.empty(n, dtype=torch.float64, device=data.X.device)
     from ._engine import _lib_metric
     _lib.call("eb_feat_one_to_all", ptr(data.X), n, data.n_features, data.dt,
               _lib_metric(metric.kind), ptr(center.X), ptr(out), stream_ptr())
     return out
-
-
-def _trace0(center):
-    # a 1-element D2H; only used on the convenience one-vs-all path, never in the device loops
-    return float(center.traces[:1].cpu()[0])
 
 
 def one_to_all(metric, X, y, out=None):
@@ -109,12 +105,13 @@ def centers_to_device(metric, cluster_centers, like):
 
 
 def assign_device(metric, data, centers, frame_idx=None, out_dist=None, out_assign=None,
-                  accumulate=False):
-    """Nearest-centre pass on the device.  Returns (dist tensor, assign int32 tensor)."""
+                  accumulate=False, scatter=False, n_idx=None, k=None):
+    """Nearest-centre pass on the device.  Returns (dist tensor, assign int32 tensor).
+    ``scatter``: out arrays are full length and frame f's result goes to position f."""
     n = len(data)
     dev = data.xyz.device if metric.is_rmsd else data.X.device
-    m = n if frame_idx is None else int(frame_idx.numel())
-    k = len(centers)
+    m = n if frame_idx is None else int(frame_idx.numel() if n_idx is None else n_idx)
+    k = len(centers) if k is None else int(k)
     dt = torch.float32 if metric.is_rmsd else torch.float64
     if out_dist is None:
         out_dist = torch.full((m,), float("inf"), dtype=dt, device=dev)
@@ -124,12 +121,12 @@ def assign_device(metric, data, centers, frame_idx=None, out_dist=None, out_assi
     if metric.is_rmsd:
         _lib.call("eb_rmsd_assign", ptr(data.xyz), ptr(data.traces), n, data.n_atoms,
                   ptr(centers.xyz), ptr(centers.traces), k, ptr(frame_idx), m, ptr(out_dist),
-                  ptr(out_assign), int(accumulate), stream_ptr())
+                  ptr(out_assign), int(accumulate), int(scatter), stream_ptr())
     else:
         from ._engine import _lib_metric
         _lib.call("eb_feat_assign", ptr(data.X), n, data.n_features, data.dt,
                   _lib_metric(metric.kind), ptr(centers.X), k, ptr(frame_idx), m,
-                  ptr(out_dist), ptr(out_assign), int(accumulate), stream_ptr())
+                  ptr(out_dist), ptr(out_assign), int(accumulate), int(scatter), stream_ptr())
     return out_dist, out_assign
 
 

@@ -1,0 +1,229 @@
+"""Device-resident PAM (k-medoids) sweeps.
+
+Reference: /root/reference/enspara/cluster/kmedoids.py:520-699 (_kmedoids_pam_update) and
+:482-517 (_propose_new_center_amongst).  Distances, assignments, the trial copies of both and
+the medoid coordinates stay in HBM for the whole run; per proposal the host only draws the
+random number (the reference's legacy ``RandomState`` stream must be consumed identically,
+SURVEY.md App. A.5) and reads back three scalars (proposed index, number of frames needing a
+full re-assignment, trial cost).
+
+Sharded runs (one process per GPU, contiguous frame blocks): member counts are all-gathered,
+every rank draws the same number from an identically seeded RandomState, the owner of the
+selected member publishes the frame with one broadcast, every rank does its local pass, and the
+trial cost is one float64 all-reduce -- so every rank takes the same accept decision.  The k-th
+member is counted in GLOBAL frame order, which makes a sharded run equal to the serial one
+(the reference's ``mpi.ops.randind`` maps the draw through a striped concatenation instead,
+mpi/ops.py:256-268; that alternative map is available as ``striped_randind=True``).
+"""
+import numpy as np
+import torch
+from sklearn.utils import check_random_state
+
+from .. import _lib
+from ..device import DeviceFeatures, DeviceTrajectory, ptr, stream_ptr
+from ..exception import DataInvalid
+from . import _ops
+from ._engine import ShardInfo
+
+
+class PamEngine:
+    def __init__(self, data, metric, comm, distances, assignments, medoid_global_inds):
+        self.data = data
+        self.metric = metric
+        self.comm = comm
+        self.lib = _lib.load()
+        self.n = len(data)
+        self.is_rmsd = metric.is_rmsd
+        self.dev = data.xyz.device if self.is_rmsd else data.X.device
+        self.shard = ShardInfo(self.n, comm)
+        self.ddt = torch.float32 if self.is_rmsd else torch.float64
+        dev = self.dev
+        self.dist = self._to_dev(distances, self.ddt)
+        self.assign = self._to_dev(assignments, torch.int32)
+        self.new_dist = torch.empty_like(self.dist)
+        self.new_assign = torch.empty_like(self.assign)
+        self.new_ctr_dist = torch.empty_like(self.dist)
+        self.ambig_idx = torch.empty(max(self.n, 1), dtype=torch.int64, device=dev)
+        # scalars read back per proposal: [proposed local index, n_ambig] and [cost numerator]
+        self.scal_i = torch.zeros(2, dtype=torch.int64, device=dev)
+        self.scal_d = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.scratch = torch.empty(int(self.lib.eb_pam_scratch_bytes(self.n)),
+                                   dtype=torch.uint8, device=dev)
+        self.k = len(medoid_global_inds)
+        self.counts = torch.zeros(max(self.k, 1), dtype=torch.int64, device=dev)
+        self.medoid_global = [int(g) for g in medoid_global_inds]
+        self.medoids = self._fetch_frames(self.medoid_global)
+        self.prop = self._fetch_frames([])  # 1-frame scratch, filled per proposal
+        self.cost_num = self._sumsq(self.dist)
+        self.n_global = self.shard.n_global
+
+    # -- helpers -------------------------------------------------------------------------
+    def _to_dev(self, arr, dtype):
+        if torch.is_tensor(arr):
+            return arr.to(device=self.dev, dtype=dtype).clone()
+        a = np.ascontiguousarray(np.asarray(arr))
+        if len(a) != self.n:
+            raise DataInvalid("length mismatch: %d values for %d frames" % (len(a), self.n))
+        return torch.from_numpy(a).to(self.dev).to(dtype)
+
+    def _empty_frames(self, m):
+        if self.is_rmsd:
+            return DeviceTrajectory.empty(m, self.data.n_atoms, self.data.top)
+        return DeviceFeatures(torch.zeros((m, self.data.n_features), dtype=self.data.X.dtype,
+                                          device=self.dev))
+
+    def _fetch_frames(self, global_inds):
+        """Dense device copy of the frames with these GLOBAL indices on every rank."""
+        m = len(global_inds)
+        out = self._empty_frames(max(m, 1))
+        if m == 0:
+            return out
+        sh = self.shard
+        mine = [(j, g - sh.offset) for j, g in enumerate(global_inds)
+                if sh.offset <= g < sh.offset + self.n]
+        if sh.size > 1:
+            if self.is_rmsd:
+                out.xyz.zero_()
+                out.traces.zero_()
+            else:
+                out.X.zero_()
+        if mine:
+            loc = torch.as_tensor([l for _, l in mine], dtype=torch.int64, device=self.dev)
+            pos = torch.as_tensor([j for j, _ in mine], dtype=torch.int64, device=self.dev)
+            if self.is_rmsd:
+                sub = self.data.gather(loc)
+                out.xyz[pos] = sub.xyz
+                out.traces[pos] = sub.traces
+            else:
+                out.X[pos] = self.data.X[loc]
+        if sh.size > 1:
+            if self.is_rmsd:
+                self.comm.all_reduce_sum(out.xyz)
+                self.comm.all_reduce_sum(out.traces)
+            else:
+                self.comm.all_reduce_sum(out.X)
+        return out
+
+    def _sumsq(self, vec):
+        _lib.call("eb_sum_squares", ptr(vec), self.n, int(not self.is_rmsd), ptr(self.scal_d),
+                  ptr(self.scratch), stream_ptr())
+        t = self.scal_d.clone()
+        self.comm.all_reduce_sum(t)
+        return float(t.cpu()[0])
+
+    def _member_counts(self, cid):
+        """Per-rank member counts of cluster cid (np.where(assignments == cid), :611)."""
+        _lib.call("eb_count_members", ptr(self.assign), self.n, self.k, ptr(self.counts),
+                  stream_ptr())
+        local = int(self.counts[cid].cpu())
+        return np.asarray(self.comm.all_gather_object(local), dtype=np.int64)
+
+    def _slot_copy(self, dst, j, src, i):
+        if self.is_rmsd:
+            dst.xyz[j].copy_(src.xyz[i])
+            dst.traces[j].copy_(src.traces[i])
+        else:
+            dst.X[j].copy_(src.X[i])
+
+    def _load_proposal(self, owner, local_idx_dev=None, local_idx=None):
+        """Make self.prop (1 frame) hold the proposed centre on every rank."""
+        sh = self.shard
+        if sh.rank == owner:
+            idx = local_idx_dev if local_idx_dev is not None else torch.as_tensor(
+                [int(local_idx)], dtype=torch.int64, device=self.dev)
+            if self.is_rmsd:
+                _lib.call("eb_gather_frames", ptr(self.data.xyz), ptr(self.data.traces),
+                          self.data.n_atoms, ptr(idx), 1, ptr(self.prop.xyz),
+                          ptr(self.prop.traces), stream_ptr())
+            else:
+                self.prop.X[0].copy_(self.data.X[idx[0]])
+        if sh.size > 1:
+            if self.is_rmsd:
+                self.comm.broadcast(self.prop.xyz, owner)
+                self.comm.broadcast(self.prop.traces, owner)
+            else:
+                self.comm.broadcast(self.prop.X, owner)
+
+    # -- one sweep -----------------------------------------------------------------------
+    def sweep(self, proposals=None, random_state=None, striped_randind=False, log=None):
+        """One pass over all k clusters (kmedoids.py:609-694).  ``proposals``: GLOBAL frame
+        indices, one per cluster, or None for random proposals.  Returns acceptances."""
+        rs = check_random_state(random_state)
+        sh = self.shard
+        acceptances = 0
+        for cid in range(self.k):
+            # ---- proposal (kmedoids.py:616-628, 482-517) -------------------------------
+            if proposals is None:
+                n_states = self._member_counts(cid)
+                total = int(n_states.sum())
+                if total < 1:
+                    raise ValueError("'a' cannot be empty unless no samples are taken")
+                g = int(rs.randint(total))
+                if striped_randind and sh.size > 1:
+                    concat = np.concatenate([np.arange(total)[r::sh.size]
+                                             for r in range(sh.size)])
+                    g = int(np.where(concat == g)[0][0])
+                bounds = np.concatenate([[0], np.cumsum(n_states)])
+                owner = int(np.searchsorted(bounds, g, side="right") - 1)
+                kth = g - int(bounds[owner])
+                if sh.rank == owner:
+                    _lib.call("eb_select_member", ptr(self.assign), self.n, cid, kth,
+                              ptr(self.scal_i), ptr(self.scratch), stream_ptr())
+                    self._load_proposal(owner, local_idx_dev=self.scal_i[:1])
+                else:
+                    self._load_proposal(owner)
+                prop_global = None  # resolved after the read-back below
+            else:
+                prop_global = int(proposals[cid])
+                owner, loc = sh.to_rank_local(prop_global)
+                self._load_proposal(owner, local_idx=loc)
+
+            # ---- full pass + three-way split (kmedoids.py:637-658) -------------------
+            d = _ops.one_to_all_device(self.metric, self.data, self.prop,
+                                       center_trace_dev=True, out=self.new_ctr_dist)
+            _lib.call("eb_pam_classify", ptr(d), ptr(self.dist), ptr(self.assign), self.n,
+                      int(not self.is_rmsd), cid, ptr(self.new_dist), ptr(self.new_assign),
+                      ptr(self.ambig_idx), ptr(self.scal_i[1:]), stream_ptr())
+            scal = self.scal_i.cpu()
+            n_ambig = int(scal[1])
+            if prop_global is None:
+                mine = int(scal[0]) + sh.offset if sh.rank == owner else -1
+                prop_global = max(self.comm.all_gather_object(mine)) if sh.size > 1 else mine
+
+            # ---- ambiguous frames against all medoids, proposal in slot cid (:660-670) --
+            if self.is_rmsd:
+                saved = (self.medoids.xyz[cid].clone(), self.medoids.traces[cid].clone())
+            else:
+                saved = (self.medoids.X[cid].clone(),)
+            self._slot_copy(self.medoids, cid, self.prop, 0)
+            if n_ambig > 0:
+                _ops.assign_device(self.metric, self.data, self.medoids,
+                                   frame_idx=self.ambig_idx, n_idx=n_ambig,
+                                   out_dist=self.new_dist, out_assign=self.new_assign,
+                                   accumulate=False, scatter=True, k=self.k)
+
+            # ---- accept / reject on mean-square cost (kmedoids.py:680-694) -----------------
+            new_num = self._sumsq(self.new_dist)
+            old_cost = self.cost_num / self.n_global
+            new_cost = new_num / self.n_global
+            accepted = new_cost < old_cost
+            if log is not None:
+                log.append((cid, prop_global, old_cost, new_cost, bool(accepted)))
+            if accepted:
+                self.dist, self.new_dist = self.new_dist, self.dist
+                self.assign, self.new_assign = self.new_assign, self.assign
+                self.cost_num = new_num
+                self.medoid_global[cid] = prop_global
+                acceptances += 1
+            else:
+                if self.is_rmsd:
+                    self.medoids.xyz[cid].copy_(saved[0])
+                    self.medoids.traces[cid].copy_(saved[1])
+                else:
+                    self.medoids.X[cid].copy_(saved[0])
+        self.last_cost = self.cost_num / self.n_global
+        return acceptances
+
+    def results_host(self):
+        return (self.assign.cpu().numpy().astype(np.int64),
+                self.dist.cpu().numpy().astype(np.float64))

@@ -1,0 +1,543 @@
+// K2: feature-vector distances (euclidean / manhattan / squared euclidean) replacing enspara's
+// Cython libdist, fused with the k-centers bookkeeping, plus the many-centres assignment.
+//
+// Reference behaviour reproduced bit for bit (paths under /root/reference/enspara/):
+//   geometry/libdist.pyx:122-145  _euclidean: out[i] += (X[i,j]-y[j])**2 in j order, then sqrt
+//   geometry/libdist.pyx:100-117  _manhattan: out[i] += fabs(X[i,j]-y[j]) in j order
+//   (generated C: the difference and the square are computed in the array's own C type --
+//    float for float32, promoted int for int8/16/32, long for int64 -- and added to a float64
+//    accumulator; gcc folds powf(d, 2) to d*d.)
+//   cluster/kcenters.py:243-311, 314-378, 217   the iteration and stop rule, as in K1
+//   cluster/util.py:159-205                      assign_to_nearest_center
+//
+// The float64 accumulation must keep the reference's j order to be bit-identical, so one
+// lane owns one row and walks it sequentially; coalescing comes from staging: a warp pulls a
+// tile of 32 rows x 256 bytes into shared memory with 16-byte vector loads (two rows per
+// request), padded so the per-lane 16-byte reads are bank-conflict free.  HBM bound: each row
+// byte is read once; dist (float64) is a coalesced read-modify-write.
+#include "eb_common.cuh"
+
+namespace eb {
+
+constexpr int kFeatThreads = 256;
+constexpr int kFeatWarps = kFeatThreads / 32;
+constexpr int kTileBytes = 256;                 // bytes of one row held per tile
+constexpr int kTileStride = kTileBytes + 16;    // 17 x 16 B: odd -> conflict-free LDS.128
+
+template <typename T> struct Wide { using type = T; };
+template <> struct Wide<int8_t> { using type = int; };
+template <> struct Wide<int16_t> { using type = int; };
+template <> struct Wide<int32_t> { using type = int; };
+template <> struct Wide<int64_t> { using type = long long; };
+
+// one term of the row sum, exactly as the reference's generated C computes it
+template <int METRIC> __device__ __forceinline__ double term_f32(float x, float y)
+{
+    const float d = __fsub_rn(x, y);
+    if (METRIC == EB_METRIC_MANHATTAN) return fabs((double)d);
+    return (double)__fmul_rn(d, d);
+}
+template <int METRIC> __device__ __forceinline__ double term_f64(double x, double y)
+{
+    const double d = __dsub_rn(x, y);
+    if (METRIC == EB_METRIC_MANHATTAN) return fabs(d);
+    return __dmul_rn(d, d);
+}
+template <typename T, int METRIC> __device__ __forceinline__ double term_int(T x, T y)
+{
+    using W = typename Wide<T>::type;
+    const W d = (W)x - (W)y;
+    if (METRIC == EB_METRIC_MANHATTAN) return fabs((double)d);
+    return (double)(W)(d * d);
+}
+template <typename T, int METRIC> struct Term {
+    static __device__ __forceinline__ double f(T x, T y) { return term_int<T, METRIC>(x, y); }
+};
+template <int METRIC> struct Term<float, METRIC> {
+    static __device__ __forceinline__ double f(float x, float y) { return term_f32<METRIC>(x, y); }
+};
+template <int METRIC> struct Term<double, METRIC> {
+    static __device__ __forceinline__ double f(double x, double y)
+    {
+        return term_f64<METRIC>(x, y);
+    }
+};
+
+template <int METRIC> __device__ __forceinline__ double finish(double acc)
+{
+    return METRIC == EB_METRIC_EUCLIDEAN ? sqrt(acc) : acc;
+}
+
+// Warp-cooperative: distances of rows [base, base+32) to the point y (shared memory).
+// Lane l returns the distance of row base+l (garbage when that row is >= n).
+template <typename T, int METRIC>
+__device__ __forceinline__ double warp_rows_distance(const T *__restrict__ X, long n, long F,
+                                                     long base, const T *y_sh,
+                                                     unsigned char *tile, bool vec_ok)
+{
+    const int lane = threadIdx.x & 31;
+    constexpr int EPT = kTileBytes / (int)sizeof(T);  // elements per row per tile
+    double acc = 0.0;
+    const long rows_here = min(32L, n - base);
+    for (long j0 = 0; j0 < F; j0 += EPT) {
+        const int fe = (int)min((long)EPT, F - j0);  // elements of this tile
+        if (vec_ok) {
+            // 16 lanes cover one row's 256 bytes; the warp covers two rows per request
+            const int nvec = (fe * (int)sizeof(T) + 15) >> 4;
+            const int r0 = lane >> 4, c16 = lane & 15;
+#pragma unroll 4
+            for (int r = r0; r < 32; r += 2) {
+                if (r < rows_here && c16 < nvec) {
+                    const int4 v = __ldg(reinterpret_cast<const int4 *>(
+                        reinterpret_cast<const unsigned char *>(X + (base + r) * F + j0) +
+                        16 * c16));
+                    *reinterpret_cast<int4 *>(tile + r * kTileStride + 16 * c16) = v;
+                }
+            }
+        } else {
+            for (int e = lane; e < 32 * fe; e += 32) {
+                const int r = e / fe, c = e - r * fe;
+                if (r < rows_here)
+                    reinterpret_cast<T *>(tile + r * kTileStride)[c] =
+                        __ldg(X + (base + r) * F + j0 + c);
+            }
+        }
+        __syncwarp();
+        const T *row = reinterpret_cast<const T *>(tile + lane * kTileStride);
+        constexpr int VE = 16 / (int)sizeof(T);  // elements per 16-byte read
+        int c = 0;
+        for (; c + VE <= fe; c += VE) {
+            const int4 raw = *reinterpret_cast<const int4 *>(row + c);
+            const T *v = reinterpret_cast<const T *>(&raw);
+#pragma unroll
+            for (int u = 0; u < VE; ++u)
+                acc = __dadd_rn(acc, Term<T, METRIC>::f(v[u], y_sh[j0 + c + u]));
+        }
+        for (; c < fe; ++c) acc = __dadd_rn(acc, Term<T, METRIC>::f(row[c], y_sh[j0 + c]));
+        __syncwarp();
+    }
+    return finish<METRIC>(acc);
+}
+
+enum FeatMode { kFStep = 0, kFSeed = 1, kFDistOnly = 2 };
+
+struct FeatSmem {
+    Partial red[32];
+    int flag;
+    double maxdist;
+    int64_t center_index;
+};
+
+template <typename T, int METRIC, int MODE>
+__global__ void __launch_bounds__(kFeatThreads)
+k_kcenters_step_feat(const T *__restrict__ X, long n, long F, long frame_offset,
+                     const unsigned char *cand_in, int n_cand, size_t rec_bytes, double *dist,
+                     int *assign, int n_clusters_limit, double cutoff, eb_kc_state *state,
+                     int64_t *center_list, Partial *partials, unsigned char *cand_out,
+                     const T *y_direct, double *out_only, int vec_ok)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FeatSmem *ss = reinterpret_cast<FeatSmem *>(smem_raw);
+    unsigned char *tiles = smem_raw + align16(sizeof(FeatSmem));
+    T *y_sh = reinterpret_cast<T *>(tiles + (size_t)kFeatWarps * 32 * kTileStride);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int k = 0;
+
+    if (MODE == kFStep) {
+        double cd;
+        int64_t ci;
+        const int r = pick_candidate(cand_in, n_cand, rec_bytes, cd, ci);
+        const bool active = (r >= 0) && step_active(state, n_clusters_limit, cd, cutoff, k);
+        if (!active) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                if (!state->done) {
+                    state->done = 1;
+                    state->maxdist = cd;
+                } else {
+                    state->n_noop += 1;
+                }
+            }
+            return;
+        }
+        const T *src = reinterpret_cast<const T *>(cand_in + (size_t)r * rec_bytes +
+                                                   sizeof(RecHeader));
+        for (long j = threadIdx.x; j < F; j += blockDim.x) y_sh[j] = src[j];
+        if (threadIdx.x == 0) {
+            ss->center_index = ci;
+            ss->maxdist = cd;
+        }
+        __syncthreads();
+    } else if (MODE == kFDistOnly) {
+        for (long j = threadIdx.x; j < F; j += blockDim.x) y_sh[j] = y_direct[j];
+        __syncthreads();
+    }
+
+    double best_d = -2.0;
+    int64_t best_i = INT64_MAX;
+    const long n_chunks = (n + 31) >> 5;
+    const long warps_total = (long)gridDim.x * kFeatWarps;
+    unsigned char *tile = tiles + (size_t)warp * 32 * kTileStride;
+
+    for (long chunk = (long)blockIdx.x * kFeatWarps + warp; chunk < n_chunks;
+         chunk += warps_total) {
+        const long base = chunk << 5;
+        const long row = base + lane;
+        double d = 0.0;
+        if (MODE != kFSeed)
+            d = warp_rows_distance<T, METRIC>(X, n, F, base, y_sh, tile, vec_ok != 0);
+        if (row < n) {
+            double cur;
+            if (MODE == kFSeed) {
+                cur = dist[row];
+            } else if (MODE == kFDistOnly) {
+                out_only[row] = d;
+                cur = 0.0;
+            } else {
+                const double old = dist[row];
+                if (d < old) {  // strict '<', kcenters.py:304
+                    dist[row] = d;
+                    assign[row] = k;
+                }
+                cur = (d < old) ? d : old;
+            }
+            if (cur > best_d) {
+                best_d = cur;
+                best_i = row;
+            }
+        }
+    }
+    if (MODE == kFDistOnly) return;
+
+    if (!grid_argmax_last_block(best_d, best_i, partials, state, ss->red, &ss->flag)) return;
+
+    RecHeader *out = reinterpret_cast<RecHeader *>(cand_out);
+    const bool empty = (best_i == INT64_MAX);
+    if (!empty) {
+        const T *src = X + best_i * F;
+        T *dst = reinterpret_cast<T *>(cand_out + sizeof(RecHeader));
+        for (long j = threadIdx.x; j < F; j += blockDim.x) dst[j] = src[j];
+    }
+    if (threadIdx.x == 0) {
+        out->dist = empty ? -1.0 : best_d;
+        out->index = empty ? -1 : frame_offset + best_i;
+        out->trace = 0.0;
+        out->reserved = 0;
+        if (MODE == kFStep) {
+            center_list[k] = ss->center_index;
+            state->n_centers = k + 1;
+            state->last_center = ss->center_index;
+            state->maxdist = ss->maxdist;
+        } else {
+            state->n_centers = n_clusters_limit;  // seed mode: carries first_center_id
+            state->done = 0;
+            state->n_noop = 0;
+            state->maxdist = 0.0;
+            state->last_center = -1;
+        }
+        state->local_maxdist = empty ? -1.0 : best_d;
+        state->blocks_done = 0;
+        __threadfence();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// many centres: every row against k centres in order, strict '<'.  A warp owns 32 rows and
+// re-stages them per centre from L1/L2 (k is small whenever this path matters for features).
+// ------------------------------------------------------------------------------------------
+template <typename T, int METRIC>
+__global__ void __launch_bounds__(kFeatThreads)
+k_feat_assign(const T *__restrict__ X, long n, long F, const T *__restrict__ centers, int k,
+              const int64_t *__restrict__ frame_idx, long m, double *out_dist, int *out_assign,
+              int accumulate, int scatter)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned char *tiles = smem_raw;
+    T *y_all = reinterpret_cast<T *>(tiles + (size_t)kFeatWarps * 32 * kTileStride);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *tile = tiles + (size_t)warp * 32 * kTileStride;
+    T *y_sh = y_all + (size_t)warp * F;  // one staged centre per warp
+    const long n_chunks = (m + 31) >> 5;
+    const long warps_total = (long)gridDim.x * kFeatWarps;
+    constexpr int EPT = kTileBytes / (int)sizeof(T);
+
+    for (long chunk = (long)blockIdx.x * kFeatWarps + warp; chunk < n_chunks;
+         chunk += warps_total) {
+        const long item = (chunk << 5) + lane;
+        const bool valid = item < m;
+        const long row = valid ? (frame_idx ? frame_idx[item] : item) : 0;
+        double best_d = INFINITY;
+        int best_c = 0;
+        const long opos = scatter ? row : item;  // where this row's result lives
+        if (valid && accumulate) {
+            best_d = out_dist[opos];
+            best_c = out_assign[opos];
+        }
+        const bool single_tile = (F <= EPT);  // the whole row fits one staged tile
+        if (single_tile) {
+            for (int e = lane; e < 32 * (int)F; e += 32) {
+                const int r = e / (int)F, cc = e - r * (int)F;
+                const long it = (chunk << 5) + r;
+                if (it < m) {
+                    const long rr = frame_idx ? frame_idx[it] : it;
+                    reinterpret_cast<T *>(tile + r * kTileStride)[cc] = __ldg(X + rr * F + cc);
+                }
+            }
+        }
+        for (int c = 0; c < k; ++c) {
+            __syncwarp();
+            for (long j = lane; j < F; j += 32) y_sh[j] = __ldg(centers + (size_t)c * F + j);
+            __syncwarp();
+            double acc = 0.0;
+            const T *rowp = reinterpret_cast<const T *>(tile + lane * kTileStride);
+            if (single_tile) {
+                for (int cc = 0; cc < (int)F; ++cc)
+                    acc = __dadd_rn(acc, Term<T, METRIC>::f(rowp[cc], y_sh[cc]));
+            } else {
+                // gather-stage the warp's rows tile by tile (rows need not be contiguous)
+                for (long j0 = 0; j0 < F; j0 += EPT) {
+                    const int fe = (int)min((long)EPT, F - j0);
+                    for (int e = lane; e < 32 * fe; e += 32) {
+                        const int r = e / fe, cc = e - r * fe;
+                        const long it = (chunk << 5) + r;
+                        if (it < m) {
+                            const long rr = frame_idx ? frame_idx[it] : it;
+                            reinterpret_cast<T *>(tile + r * kTileStride)[cc] =
+                                __ldg(X + rr * F + j0 + cc);
+                        }
+                    }
+                    __syncwarp();
+                    for (int cc = 0; cc < fe; ++cc)
+                        acc = __dadd_rn(acc, Term<T, METRIC>::f(rowp[cc], y_sh[j0 + cc]));
+                    __syncwarp();
+                }
+            }
+            const double d = finish<METRIC>(acc);
+            if (valid && d < best_d) {
+                best_d = d;
+                best_c = c;
+            }
+        }
+        if (valid) {
+            out_dist[opos] = best_d;
+            out_assign[opos] = best_c;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side dispatch
+// ------------------------------------------------------------------------------------------
+static size_t elem_size(int dtype)
+{
+    switch (dtype) {
+        case EB_DT_F32: return 4;
+        case EB_DT_F64: return 8;
+        case EB_DT_I8: return 1;
+        case EB_DT_I16: return 2;
+        case EB_DT_I32: return 4;
+        case EB_DT_I64: return 8;
+    }
+    return 0;
+}
+
+static size_t feat_smem(long F, size_t es, int n_y)
+{
+    return align16(sizeof(FeatSmem)) + (size_t)kFeatWarps * 32 * kTileStride +
+           align16((size_t)F * es) * n_y;
+}
+
+static int feat_grid(long n, size_t smem)
+{
+    const long chunks = (n + 31) / 32;
+    long blocks = (chunks + kFeatWarps - 1) / kFeatWarps;
+    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    const long cap = (long)per_sm * sm_count();
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+template <typename T, int METRIC, int MODE>
+static int launch_feat(const void *X, long n, long F, long frame_offset, const void *cand_in,
+                       int n_cand, double *dist, int *assign, int limit, double cutoff,
+                       eb_kc_state *state, int64_t *center_list, void *partials, void *cand_out,
+                       const void *y_direct, double *out_only, cudaStream_t stream)
+{
+    const size_t smem = feat_smem(F, sizeof(T), 1);
+    if (smem > 227 * 1024)
+        return fail(EB_ERR_LIMIT, "%s: n_features=%ld needs %ld bytes of shared memory",
+                    "feature kernel", F, (long)smem);
+    auto kern = k_kcenters_step_feat<T, METRIC, MODE>;
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     227 * 1024));
+        configured = 227 * 1024;
+    }
+    const size_t rec_bytes = sizeof(RecHeader) + align16((size_t)F * sizeof(T));
+    const int vec_ok = (((size_t)F * sizeof(T)) % 16 == 0) && (((uintptr_t)X) % 16 == 0);
+    kern<<<feat_grid(n, smem), kFeatThreads, smem, stream>>>(
+        (const T *)X, n, F, frame_offset, (const unsigned char *)cand_in, n_cand, rec_bytes, dist,
+        assign, limit, cutoff, state, center_list, (Partial *)partials,
+        (unsigned char *)cand_out, (const T *)y_direct, out_only, vec_ok);
+    EB_LAUNCH_CHECK();
+    return EB_OK;
+}
+
+template <typename T, int MODE, typename... Args>
+static int dispatch_metric(int metric, Args... args)
+{
+    switch (metric) {
+        case EB_METRIC_EUCLIDEAN: return launch_feat<T, EB_METRIC_EUCLIDEAN, MODE>(args...);
+        case EB_METRIC_MANHATTAN: return launch_feat<T, EB_METRIC_MANHATTAN, MODE>(args...);
+        case EB_METRIC_SQEUCLIDEAN: return launch_feat<T, EB_METRIC_SQEUCLIDEAN, MODE>(args...);
+    }
+    return fail(EB_ERR_INVALID, "%s", "unknown metric");
+}
+
+template <int MODE, typename... Args> static int dispatch(int dtype, int metric, Args... args)
+{
+    switch (dtype) {
+        case EB_DT_F32: return dispatch_metric<float, MODE>(metric, args...);
+        case EB_DT_F64: return dispatch_metric<double, MODE>(metric, args...);
+        case EB_DT_I8: return dispatch_metric<int8_t, MODE>(metric, args...);
+        case EB_DT_I16: return dispatch_metric<int16_t, MODE>(metric, args...);
+        case EB_DT_I32: return dispatch_metric<int32_t, MODE>(metric, args...);
+        case EB_DT_I64: return dispatch_metric<int64_t, MODE>(metric, args...);
+    }
+    return fail(EB_ERR_INVALID, "%s", "unknown dtype");
+}
+
+template <typename T, int METRIC>
+static int launch_assign(const void *X, long n, long F, const void *centers, int k,
+                         const int64_t *frame_idx, long m, double *out_dist, int *out_assign,
+                         int accumulate, int scatter, cudaStream_t stream)
+{
+    const size_t smem = (size_t)kFeatWarps * 32 * kTileStride +
+                        align16((size_t)F * sizeof(T)) * kFeatWarps;
+    if (smem > 227 * 1024)
+        return fail(EB_ERR_LIMIT, "%s: n_features=%ld needs %ld bytes of shared memory",
+                    "feat_assign", F, (long)smem);
+    auto kern = k_feat_assign<T, METRIC>;
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     227 * 1024));
+        configured = 227 * 1024;
+    }
+    kern<<<feat_grid(m, smem), kFeatThreads, smem, stream>>>(
+        (const T *)X, n, F, (const T *)centers, k, frame_idx, m, out_dist, out_assign, accumulate,
+        scatter);
+    EB_LAUNCH_CHECK();
+    return EB_OK;
+}
+
+template <typename T, typename... Args> static int dispatch_assign_metric(int metric, Args... args)
+{
+    switch (metric) {
+        case EB_METRIC_EUCLIDEAN: return launch_assign<T, EB_METRIC_EUCLIDEAN>(args...);
+        case EB_METRIC_MANHATTAN: return launch_assign<T, EB_METRIC_MANHATTAN>(args...);
+        case EB_METRIC_SQEUCLIDEAN: return launch_assign<T, EB_METRIC_SQEUCLIDEAN>(args...);
+    }
+    return fail(EB_ERR_INVALID, "%s", "unknown metric");
+}
+
+}  // namespace eb
+
+using namespace eb;
+
+extern "C" {
+
+size_t eb_feat_record_bytes(int64_t n_features, int dtype)
+{
+    return sizeof(RecHeader) + align16((size_t)n_features * elem_size(dtype));
+}
+
+int eb_kcenters_step_feat(const void *X, int64_t n, int64_t n_features, int dtype, int metric,
+                          int64_t frame_offset, const void *cand_in, int n_cand, double *dist,
+                          int32_t *assign, int32_t n_clusters_limit, double dist_cutoff,
+                          eb_kc_state *state, int64_t *center_list, void *partials,
+                          void *cand_out, void *stream)
+{
+    EB_CHECK_ARG(n >= 0 && n_features > 0, "kcenters_step_feat: bad shape");
+    EB_CHECK_ARG(elem_size(dtype) != 0, "kcenters_step_feat: unknown dtype");
+    EB_CHECK_ARG(n_cand >= 1 && cand_in && cand_out && state && partials && center_list,
+                 "kcenters_step_feat: null pointer / n_cand < 1");
+    return dispatch<kFStep>(dtype, metric, X, (long)n, (long)n_features, (long)frame_offset,
+                            cand_in, n_cand, dist, assign, (int)n_clusters_limit, dist_cutoff,
+                            state, center_list, partials, cand_out, (const void *)nullptr,
+                            (double *)nullptr, (cudaStream_t)stream);
+}
+
+int eb_kcenters_seed_feat(const void *X, int64_t n, int64_t n_features, int dtype,
+                          int64_t frame_offset, const double *dist, int32_t first_center_id,
+                          eb_kc_state *state, void *partials, void *cand_out, void *stream)
+{
+    EB_CHECK_ARG(n >= 0 && n_features > 0, "kcenters_seed_feat: bad shape");
+    EB_CHECK_ARG(elem_size(dtype) != 0, "kcenters_seed_feat: unknown dtype");
+    EB_CHECK_ARG(state && partials && cand_out, "kcenters_seed_feat: null pointer");
+    EB_CUDA(cudaMemsetAsync(state, 0, sizeof(eb_kc_state), (cudaStream_t)stream));
+    return dispatch<kFSeed>(dtype, EB_METRIC_EUCLIDEAN, X, (long)n, (long)n_features,
+                            (long)frame_offset, (const void *)nullptr, 0,
+                            const_cast<double *>(dist), (int *)nullptr, (int)first_center_id,
+                            0.0, state, (int64_t *)nullptr, partials, cand_out,
+                            (const void *)nullptr, (double *)nullptr, (cudaStream_t)stream);
+}
+
+int eb_feat_one_to_all(const void *X, int64_t n, int64_t n_features, int dtype, int metric,
+                       const void *y, double *out, void *stream)
+{
+    EB_CHECK_ARG(n >= 0 && n_features > 0, "feat_one_to_all: bad shape");
+    EB_CHECK_ARG(elem_size(dtype) != 0, "feat_one_to_all: unknown dtype");
+    if (n == 0) return EB_OK;
+    EB_CHECK_ARG(X && y && out, "feat_one_to_all: null pointer");
+    return dispatch<kFDistOnly>(dtype, metric, X, (long)n, (long)n_features, 0L,
+                                (const void *)nullptr, 0, (double *)nullptr, (int *)nullptr, 0,
+                                0.0, (eb_kc_state *)nullptr, (int64_t *)nullptr,
+                                (void *)nullptr, (void *)nullptr, y, out, (cudaStream_t)stream);
+}
+
+int eb_feat_assign(const void *X, int64_t n, int64_t n_features, int dtype, int metric,
+                   const void *centers, int32_t k, const int64_t *frame_idx, int64_t n_idx,
+                   double *out_dist, int32_t *out_assign, int accumulate, int scatter,
+                   void *stream)
+{
+    EB_CHECK_ARG(n >= 0 && n_features > 0 && k >= 0 && n_idx >= 0, "feat_assign: bad shape");
+    EB_CHECK_ARG(elem_size(dtype) != 0, "feat_assign: unknown dtype");
+    const long m = frame_idx ? n_idx : n;
+    if (m == 0 || k == 0) return EB_OK;
+    EB_CHECK_ARG(X && centers && out_dist && out_assign, "feat_assign: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (dtype) {
+        case EB_DT_F32:
+            return dispatch_assign_metric<float>(metric, X, (long)n, (long)n_features, centers,
+                                                 (int)k, frame_idx, m, out_dist, out_assign,
+                                                 accumulate, scatter, s);
+        case EB_DT_F64:
+            return dispatch_assign_metric<double>(metric, X, (long)n, (long)n_features, centers,
+                                                  (int)k, frame_idx, m, out_dist, out_assign,
+                                                  accumulate, scatter, s);
+        case EB_DT_I8:
+            return dispatch_assign_metric<int8_t>(metric, X, (long)n, (long)n_features, centers,
+                                                  (int)k, frame_idx, m, out_dist, out_assign,
+                                                  accumulate, scatter, s);
+        case EB_DT_I16:
+            return dispatch_assign_metric<int16_t>(metric, X, (long)n, (long)n_features, centers,
+                                                   (int)k, frame_idx, m, out_dist, out_assign,
+                                                   accumulate, scatter, s);
+        case EB_DT_I32:
+            return dispatch_assign_metric<int32_t>(metric, X, (long)n, (long)n_features, centers,
+                                                   (int)k, frame_idx, m, out_dist, out_assign,
+                                                   accumulate, scatter, s);
+        case EB_DT_I64:
+            return dispatch_assign_metric<int64_t>(metric, X, (long)n, (long)n_features, centers,
+                                                   (int)k, frame_idx, m, out_dist, out_assign,
+                                                   accumulate, scatter, s);
+    }
+    return fail(EB_ERR_INVALID, "%s", "unknown dtype");
+}
+
+}  // extern "C"

@@ -1,0 +1,256 @@
+// K4 / K6: the n-length bookkeeping of one PAM proposal, on device vectors.
+//
+// Reference behaviour reproduced (paths under /root/reference/enspara/):
+//   cluster/kmedoids.py:639-658  three-way split after the full-pass distance to the proposal:
+//        dn       = distances >  new   -> (cid, new)
+//        up_other = distances <= new and assign != cid -> unchanged
+//        up_this  = distances <= new and assign == cid -> needs the nearest of ALL medoids
+//   cluster/kmedoids.py:478-479  cost = mean(d^2) (numerator here; deterministic order)
+//   cluster/kmedoids.py:611,514  state_inds = where(assign == cid)[0]; choice(state_inds)
+//        == state_inds[randint(len(state_inds))]  -> count + k-th member select
+// All kernels are HBM bound over 4..8-byte-per-frame vectors; they exist so that distances and
+// assignments never leave the device between proposals.
+#include "eb_common.cuh"
+
+namespace eb {
+
+constexpr int kPamThreads = 256;
+constexpr int kPamMaxBlocks = 2048;
+
+template <typename D>
+__global__ void __launch_bounds__(kPamThreads)
+k_pam_classify(const D *__restrict__ new_ctr_dist, const D *__restrict__ dist,
+               const int *__restrict__ assign, long n, int cid, D *__restrict__ new_dist,
+               int *__restrict__ new_assign, int64_t *__restrict__ ambig_idx,
+               unsigned long long *n_ambig)
+{
+    const int lane = threadIdx.x & 31;
+    const long stride = (long)gridDim.x * blockDim.x;
+    const long n_round = (n + 31) & ~31L;  // keep whole warps in the loop for the ballot
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        bool ambig = false;
+        if (i < n) {
+            const D dn = new_ctr_dist[i];
+            const D d_old = dist[i];
+            const int a = assign[i];
+            if (d_old > dn) {
+                new_assign[i] = cid;
+                new_dist[i] = dn;
+            } else if (a != cid) {
+                new_assign[i] = a;
+                new_dist[i] = d_old;
+            } else {
+                ambig = true;
+                new_assign[i] = -1;
+                new_dist[i] = (D)-1;
+            }
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, ambig);
+        if (mask) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(n_ambig, (unsigned long long)__popc(mask));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (ambig) ambig_idx[base + __popc(mask & ((1u << lane) - 1))] = i;
+        }
+    }
+}
+
+// deterministic sum of squares: fixed block ranges, fixed tree, ordered final pass
+template <typename D>
+__global__ void __launch_bounds__(kPamThreads)
+k_sumsq_partial(const D *__restrict__ x, long n, double *__restrict__ partials)
+{
+    __shared__ double sh[kPamThreads];
+    const long per_block = (n + gridDim.x - 1) / gridDim.x;
+    const long lo = (long)blockIdx.x * per_block;
+    const long hi = min(n, lo + per_block);
+    double s = 0.0;
+    for (long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const double v = (double)x[i];
+        s = fma(v, v, s);
+    }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = kPamThreads / 2; w > 0; w >>= 1) {
+        if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partials[blockIdx.x] = sh[0];
+}
+
+__global__ void k_sum_final(const double *__restrict__ partials, int nb, double *out)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int b = 0; b < nb; ++b) s += partials[b];
+        *out = s;
+    }
+}
+
+__global__ void __launch_bounds__(kPamThreads)
+k_count_members(const int *__restrict__ assign, long n, int k, unsigned long long *counts)
+{
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int a = assign[i];
+        if (a >= 0 && a < k) atomicAdd(counts + a, 1ULL);
+    }
+}
+
+// k-th member select, pass 1: members per fixed block range
+__global__ void __launch_bounds__(kPamThreads)
+k_select_count(const int *__restrict__ assign, long n, int cid, long per_block,
+               unsigned long long *block_counts)
+{
+    __shared__ unsigned int sh;
+    if (threadIdx.x == 0) sh = 0;
+    __syncthreads();
+    const long lo = (long)blockIdx.x * per_block;
+    const long hi = min(n, lo + per_block);
+    unsigned int c = 0;
+    for (long i = lo + threadIdx.x; i < hi; i += blockDim.x) c += (assign[i] == cid);
+    for (int m = 16; m > 0; m >>= 1) c += __shfl_xor_sync(0xffffffffu, c, m);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&sh, c);
+    __syncthreads();
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = sh;
+}
+
+// pass 2 (one warp): find the block holding the kth member, then walk that block's range
+__global__ void k_select_pick(const int *__restrict__ assign, long n, int cid, long kth,
+                              long per_block, const unsigned long long *block_counts, int nb,
+                              int64_t *out)
+{
+    const int lane = threadIdx.x;
+    __shared__ long s_block, s_rem;
+    if (lane == 0) {
+        long rem = kth;
+        int b = 0;
+        for (; b < nb; ++b) {
+            const long c = (long)block_counts[b];
+            if (rem < c) break;
+            rem -= c;
+        }
+        s_block = b;
+        s_rem = rem;
+    }
+    __syncwarp();
+    if (s_block >= nb) {
+        if (lane == 0) *out = -1;
+        return;
+    }
+    const long lo = s_block * per_block;
+    const long hi = min(n, lo + per_block);
+    long rem = s_rem;
+    for (long base = lo; base < hi; base += 32) {
+        const long i = base + lane;
+        const bool hit = (i < hi) && (assign[i] == cid);
+        const unsigned mask = __ballot_sync(0xffffffffu, hit);
+        const int c = __popc(mask);
+        if (rem < c) {
+            // the (rem)-th set bit of mask
+            unsigned mm = mask;
+            for (long t = 0; t < rem; ++t) mm &= mm - 1;
+            if (lane == 0) *out = base + (__ffs(mm) - 1);
+            return;
+        }
+        rem -= c;
+    }
+    if (lane == 0) *out = -1;
+}
+
+static int pam_blocks(long n)
+{
+    long b = (n + kPamThreads * 4 - 1) / (kPamThreads * 4);
+    const long cap = 8L * sm_count();
+    if (b > cap) b = cap;
+    if (b > kPamMaxBlocks) b = kPamMaxBlocks;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+}  // namespace eb
+
+using namespace eb;
+
+extern "C" {
+
+size_t eb_pam_scratch_bytes(int64_t n)
+{
+    (void)n;
+    return sizeof(double) * kPamMaxBlocks;
+}
+
+int eb_pam_classify(const void *new_ctr_dist, const void *dist, const int32_t *assign, int64_t n,
+                    int dist_is_f64, int32_t cid, void *new_dist, int32_t *new_assign,
+                    int64_t *ambig_idx, int64_t *n_ambig, void *stream)
+{
+    EB_CHECK_ARG(n >= 0, "pam_classify: n < 0");
+    EB_CHECK_ARG(n_ambig, "pam_classify: null counter");
+    cudaStream_t s = (cudaStream_t)stream;
+    EB_CUDA(cudaMemsetAsync(n_ambig, 0, sizeof(int64_t), s));
+    if (n == 0) return EB_OK;
+    EB_CHECK_ARG(new_ctr_dist && dist && assign && new_dist && new_assign && ambig_idx,
+                 "pam_classify: null pointer");
+    if (dist_is_f64)
+        k_pam_classify<double><<<pam_blocks(n), kPamThreads, 0, s>>>(
+            (const double *)new_ctr_dist, (const double *)dist, assign, n, cid,
+            (double *)new_dist, new_assign, ambig_idx, (unsigned long long *)n_ambig);
+    else
+        k_pam_classify<float><<<pam_blocks(n), kPamThreads, 0, s>>>(
+            (const float *)new_ctr_dist, (const float *)dist, assign, n, cid, (float *)new_dist,
+            new_assign, ambig_idx, (unsigned long long *)n_ambig);
+    EB_LAUNCH_CHECK();
+    return EB_OK;
+}
+
+int eb_sum_squares(const void *dist, int64_t n, int dist_is_f64, double *out, void *scratch,
+                   void *stream)
+{
+    EB_CHECK_ARG(n >= 0 && out && scratch, "sum_squares: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) {
+        EB_CUDA(cudaMemsetAsync(out, 0, sizeof(double), s));
+        return EB_OK;
+    }
+    const int nb = pam_blocks(n);
+    if (dist_is_f64)
+        k_sumsq_partial<double><<<nb, kPamThreads, 0, s>>>((const double *)dist, n,
+                                                           (double *)scratch);
+    else
+        k_sumsq_partial<float><<<nb, kPamThreads, 0, s>>>((const float *)dist, n,
+                                                          (double *)scratch);
+    EB_LAUNCH_CHECK();
+    k_sum_final<<<1, 32, 0, s>>>((const double *)scratch, nb, out);
+    EB_LAUNCH_CHECK();
+    return EB_OK;
+}
+
+int eb_count_members(const int32_t *assign, int64_t n, int32_t k, int64_t *counts, void *stream)
+{
+    EB_CHECK_ARG(n >= 0 && k >= 0 && counts, "count_members: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    EB_CUDA(cudaMemsetAsync(counts, 0, sizeof(int64_t) * (size_t)k, s));
+    if (n == 0 || k == 0) return EB_OK;
+    k_count_members<<<pam_blocks(n), kPamThreads, 0, s>>>(assign, n, k,
+                                                          (unsigned long long *)counts);
+    EB_LAUNCH_CHECK();
+    return EB_OK;
+}
+
+int eb_select_member(const int32_t *assign, int64_t n, int32_t cid, int64_t kth, int64_t *out,
+                     void *scratch, void *stream)
+{
+    EB_CHECK_ARG(n >= 0 && kth >= 0 && out && scratch, "select_member: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nb = pam_blocks(n);
+    const long per_block = (n + nb - 1) / nb;
+    k_select_count<<<nb, kPamThreads, 0, s>>>(assign, n, cid, per_block,
+                                              (unsigned long long *)scratch);
+    EB_LAUNCH_CHECK();
+    k_select_pick<<<1, 32, 0, s>>>(assign, n, cid, kth, per_block,
+                                   (const unsigned long long *)scratch, nb, out);
+    EB_LAUNCH_CHECK();
+    return EB_OK;
+}
+
+}  // extern "C"

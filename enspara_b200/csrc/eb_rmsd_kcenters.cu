@@ -142,7 +142,7 @@ k_kcenters_step_rmsd(const float *__restrict__ xyz, const double *__restrict__ t
                      int n_cand, size_t rec_bytes, float *dist, int *assign,
                      int n_clusters_limit, double cutoff, eb_kc_state *state,
                      int64_t *center_list, Partial *partials, unsigned char *cand_out,
-                     const float *center_direct, double center_trace_direct, float *out_only)
+                     const float *center_direct, const double *center_trace_direct, float *out_only)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StepSmem *ss = reinterpret_cast<StepSmem *>(smem_raw);
@@ -183,7 +183,7 @@ k_kcenters_step_rmsd(const float *__restrict__ xyz, const double *__restrict__ t
         }
         __syncthreads();
     } else if (MODE == kModeDistOnly) {
-        Gb = center_trace_direct;
+        Gb = __ldg(center_trace_direct);
         center_smem_fill(cs, center_direct, A_pad);
         __syncthreads();
     }
@@ -300,8 +300,8 @@ static int launch_step(const float *xyz, const double *traces, long n, int A, lo
                        const void *cand_in, int n_cand, float *dist, int *assign,
                        int n_clusters_limit, double cutoff, eb_kc_state *state,
                        int64_t *center_list, void *partials, void *cand_out,
-                       const float *center_direct, double center_trace_direct, float *out_only,
-                       cudaStream_t stream)
+                       const float *center_direct, const double *center_trace_direct,
+                       float *out_only, cudaStream_t stream)
 {
     const int A_pad = rmsd_apad(A);
     const size_t smem = step_smem_bytes(A_pad);
@@ -404,11 +404,11 @@ int eb_kcenters_step_rmsd(const float *xyz_soa, const double *traces, int64_t n,
     if (exact)
         return launch_step<true, kModeStep>(xyz_soa, traces, n, n_atoms, frame_offset, cand_in,
                                             n_cand, dist, assign, n_clusters_limit, dist_cutoff,
-                                            state, center_list, partials, cand_out, nullptr, 0.0,
+                                            state, center_list, partials, cand_out, nullptr, nullptr,
                                             nullptr, (cudaStream_t)stream);
     return launch_step<false, kModeStep>(xyz_soa, traces, n, n_atoms, frame_offset, cand_in,
                                          n_cand, dist, assign, n_clusters_limit, dist_cutoff,
-                                         state, center_list, partials, cand_out, nullptr, 0.0,
+                                         state, center_list, partials, cand_out, nullptr, nullptr,
                                          nullptr, (cudaStream_t)stream);
 }
 
@@ -422,17 +422,18 @@ int eb_kcenters_seed_rmsd(const float *xyz_soa, const double *traces, int64_t n,
     return launch_step<true, kModeSeed>(xyz_soa, traces, n, n_atoms, frame_offset, nullptr, 0,
                                         const_cast<float *>(dist), nullptr, first_center_id, 0.0,
                                         state,
-                                        nullptr, partials, cand_out, nullptr, 0.0, nullptr,
+                                        nullptr, partials, cand_out, nullptr, nullptr, nullptr,
                                         (cudaStream_t)stream);
 }
 
 int eb_rmsd_one_to_all(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
-                       const float *center_soa, double center_trace, float *out, int exact,
-                       void *stream)
+                       const float *center_soa, const double *center_trace, float *out,
+                       int exact, void *stream)
 {
     EB_CHECK_ARG(n >= 0 && n_atoms > 0, "rmsd_one_to_all: bad shape");
     if (n == 0) return EB_OK;
-    EB_CHECK_ARG(xyz_soa && traces && center_soa && out, "rmsd_one_to_all: null pointer");
+    EB_CHECK_ARG(xyz_soa && traces && center_soa && center_trace && out,
+                 "rmsd_one_to_all: null pointer");
     if (exact)
         return launch_step<true, kModeDistOnly>(xyz_soa, traces, n, n_atoms, 0, nullptr, 0,
                                                 nullptr, nullptr, 0, 0.0, nullptr, nullptr,

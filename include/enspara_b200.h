@@ -119,12 +119,25 @@ int eb_kcenters_step_rmsd(const float *xyz_soa, const double *traces, int64_t n,
 int eb_kcenters_seed_rmsd(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
                           int64_t frame_offset, const float *dist, int32_t first_center_id,
                           eb_kc_state *state, void *partials, void *cand_out, void *stream);
-/* one-vs-all RMSD only (the md.rmsd(traj, frame) call itself, util.py:290): out float32[n] */
+/* one-vs-all RMSD only (the md.rmsd(traj, frame) call itself, util.py:290): out float32[n];
+ * center_trace points at the centre's trace in device memory */
 int eb_rmsd_one_to_all(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
-                       const float *center_soa, double center_trace, float *out, int exact,
-                       void *stream);
+                       const float *center_soa, const double *center_trace, float *out,
+                       int exact, void *stream);
 
-#ifdef EB_PLANNED /* declared ahead of their implementation; not exported yet */
+/* ---- K3: many-centres nearest-centre assignment (cluster/util.py:159-205) ---------------
+ * For every frame the nearest of k centres, strict '<' in centre order (lowest centre index
+ * wins ties), starting from dist/assign as given when `accumulate` != 0, else from +inf / 0.
+ * frame_idx (optional, may be NULL) restricts the pass to a subset of local frames -- the
+ * X[dst_up_assig_this] re-assignment of kmedoids.py:666-667.  With scatter == 0 out_dist /
+ * out_assign have one entry per visited frame, in visiting order (length n_idx, or n when
+ * frame_idx is NULL); with scatter != 0 they are full-length arrays and the result of frame f
+ * is written at position f (the new_dist[mask] = ... scatter of kmedoids.py:669-670). */
+int eb_rmsd_assign(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
+                   const float *centers_soa, const double *center_traces, int32_t k,
+                   const int64_t *frame_idx, int64_t n_idx, float *out_dist,
+                   int32_t *out_assign, int accumulate, int scatter, void *stream);
+
 size_t eb_feat_record_bytes(int64_t n_features, int dtype);
 /* ---- K2: fused k-centers step, feature vectors (libdist.pyx:100-145) -------------------
  * X is (n, F) row-major of `dtype`; dist is float64 like libdist's output; arithmetic follows
@@ -142,19 +155,11 @@ int eb_kcenters_seed_feat(const void *X, int64_t n, int64_t n_features, int dtyp
 int eb_feat_one_to_all(const void *X, int64_t n, int64_t n_features, int dtype, int metric,
                        const void *y, double *out, void *stream);
 
-/* ---- K3: many-centres nearest-centre assignment (cluster/util.py:159-205) ---------------
- * For every frame the nearest of k centres, strict '<' in centre order (lowest centre index
- * wins ties), starting from dist/assign as given when `accumulate` != 0, else from +inf / 0.
- * frame_idx (optional, may be NULL) restricts the pass to a subset of local frames -- the
- * X[dst_up_assig_this] re-assignment of kmedoids.py:666-667.  Results are written at the
- * subset positions of out_dist/out_assign (dense when frame_idx is NULL). */
-int eb_rmsd_assign(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
-                   const float *centers_soa, const double *center_traces, int32_t k,
-                   const int64_t *frame_idx, int64_t n_idx, float *out_dist,
-                   int32_t *out_assign, int accumulate, void *stream);
+/* ---- K3 for feature vectors (same contract as eb_rmsd_assign) */
 int eb_feat_assign(const void *X, int64_t n, int64_t n_features, int dtype, int metric,
                    const void *centers, int32_t k, const int64_t *frame_idx, int64_t n_idx,
-                   double *out_dist, int32_t *out_assign, int accumulate, void *stream);
+                   double *out_dist, int32_t *out_assign, int accumulate, int scatter,
+                   void *stream);
 
 /* ---- K4/K6: PAM bookkeeping (cluster/kmedoids.py:611-694) -------------------------------
  * eb_pam_classify: given the full-pass distances to the proposal (new_ctr_dist) builds
@@ -166,7 +171,7 @@ int eb_feat_assign(const void *X, int64_t n, int64_t n_features, int dtype, int 
  * DT = 0 for float32 distance arrays (RMSD), 1 for float64 (feature metrics). */
 int eb_pam_classify(const void *new_ctr_dist, const void *dist, const int32_t *assign, int64_t n,
                     int dist_is_f64, int32_t cid, void *new_dist, int32_t *new_assign,
-                    int64_t *ambig_idx, int64_t *n_ambig, void *scratch, void *stream);
+                    int64_t *ambig_idx, int64_t *n_ambig, void *stream);
 size_t eb_pam_scratch_bytes(int64_t n);
 int eb_sum_squares(const void *dist, int64_t n, int dist_is_f64, double *out, void *scratch,
                    void *stream);
@@ -174,6 +179,7 @@ int eb_count_members(const int32_t *assign, int64_t n, int32_t k, int64_t *count
 int eb_select_member(const int32_t *assign, int64_t n, int32_t cid, int64_t kth, int64_t *out,
                      void *scratch, void *stream);
 
+#ifdef EB_PLANNED /* declared ahead of their implementation; not exported yet */
 /* ---- synthetic data: counter-based generator keyed on (seed, global frame) -
  * Writes centred SoA frames + traces directly in HBM so a 10M x 500-atom trajectory never has
  * to exist on the host.  The same generator is restated in numpy (enspara_b200/synth.py) for
