@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py -- RMSD frame-centre evaluations per second for KCenters on B200 (BASELINE.json).
+
+A "step" is ONE k-centers iteration (one pass of the fused step kernel over every resident
+frame, plus the candidate all-gather when N > 1).  Workload = BASELINE config 4's per-GPU
+shard: 1,250,000 frames x 500 atoms per GPU (7.5 GB of coordinates per GPU, >> 126 MB of L2, so
+no flush is needed between steps); N GPUs hold N such shards (weak scaling; N = 8 is the
+10M-frame north-star run).  Frames are synthetic (enspara_b200/synth.py, generated in HBM).
+
+Arms
+  default            the B200 path.  `value`: inputs resident in HBM, K steps timed with CUDA
+                     events, max over ranks.  `e2e`: the same metric through the public API
+                     (KCenters(...).fit on a HOST array: H2D + centring + K steps + D2H of the
+                     results inside the timed region).  `roofline`: per-launch event times of
+                     the step kernel against MEASURED_PEAKS.json.  `cpu_baseline`: the oracle's
+                     restated mdtraj path on the host cores, bounded sample (rank 0, N=1 only).
+  --impl reference   the reference's own CPU path for this metric (restated: mdtraj is not
+                     installable here) driven by the restated k-centers loop, all host threads.
+
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_FRAMES_PER_GPU = 1_250_000
+N_ATOMS = 500
+METRIC = "rmsd_frame_center_evals_per_s"
+UNIT = "evals/s"
+WORKLOAD = "KCenters rmsd, 1.25M frames x 500 atoms per GPU (BASELINE config 4 shard: " \
+           "10M x 500 over 8 GPUs), one k-centers iteration per step"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=50)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--frames-per-gpu", type=int, default=N_FRAMES_PER_GPU)
+    p.add_argument("--atoms", type=int, default=N_ATOMS)
+    p.add_argument("--cpu-seconds", type=float, default=12.0,
+                   help="target CPU seconds for the bounded cpu_baseline sample")
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--fast", action="store_true", help="float32-block accumulation mode")
+    return p.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.lines:
+            if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                  "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:  # region shorter than the sampling period: fall back to all samples
+            for ts, line in self.lines:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except (ValueError, IndexError):
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the reference's path for this metric, restated (oracle/), bounded sample
+# ---------------------------------------------------------------------------------------------
+def cpu_kcenters_rate(n_atoms, steps, warmup, target_seconds, sample_frames=None):
+    """Times the restated reference k-centers iteration (kcenters.py:282-309 around the
+    restated md.rmsd with its per-call copy + centre) on all host threads.  Returns
+    (evals_per_s, info dict)."""
+    from enspara_b200 import synth
+    from oracle import distances as od
+    threads = od.num_threads()
+    n = sample_frames or 100_000
+    X = synth.trajectory(n, n_atoms, seed=0)
+    T = od.Trajectory(X)
+    distances = np.full(n, np.inf)
+    assignments = np.full(n, -1, dtype=np.int64)
+    ctr = []
+
+    def iteration():
+        new = int(np.argmax(distances))
+        d = od.rmsd_f32(T, T[new])
+        upd = d < distances
+        distances[upd] = d[upd]
+        assignments[upd] = len(ctr)
+        ctr.append(new)
+        return distances.max()
+
+    for _ in range(max(1, warmup)):
+        iteration()
+    if steps is None:
+        t = time.perf_counter()
+        iteration()
+        one = time.perf_counter() - t
+        steps = int(min(50, max(3, target_seconds / max(one, 1e-6))))
+    t = time.perf_counter()
+    for _ in range(steps):
+        iteration()
+    dt = time.perf_counter() - t
+    rate = n * steps / dt
+    info = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d k-centers iterations over %d frames x %d atoms (restated mdtraj "
+                      "float32 RMSD incl. per-call copy+centre, numpy bookkeeping as "
+                      "kcenters.py:282-309; mdtraj itself is not installable offline)"
+                      % (steps, n, n_atoms),
+            "seconds": dt}
+    return rate, info, steps, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rate, info, steps, dt = cpu_kcenters_rate(args.atoms, args.steps, args.warmup,
+                                              args.cpu_seconds)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n_atoms": args.atoms,
+                   "note": "CPU arm runs a bounded sample of the same workload: "
+                           + info["sample"]},
+        "cpu_baseline": info,
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from enspara_b200 import mpi, synth
+    from enspara_b200.cluster import kcenters as kc_mod
+    from enspara_b200.cluster._engine import KCentersEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    comm = mpi.comm if world > 1 else kc_mod._SingleComm()
+
+    n_local, A = args.frames_per_gpu, args.atoms
+    n_total = n_local * world
+    K, W = args.steps, max(args.warmup, 3)
+    exact = not args.fast
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident data: this rank's shard of the global synthetic trajectory ---------------
+    data = synth.device_trajectory(n_local, A, seed=0, first_frame=rank * n_local)
+    torch.cuda.synchronize()
+
+    # ---- `value`: K steps, inputs resident in HBM ------------------------------------------
+    eng = KCentersEngine(data, "rmsd", comm, exact=exact)
+    eng._ensure_center_list(K + W + 8)
+    eng.seed(0)
+    limit = K + W + 4
+    for _ in range(W):
+        eng.step(limit, 0.0)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.3)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    barrier()
+    t0 = time.perf_counter()
+    ev[0].record()
+    for i in range(K):
+        eng.step(limit, 0.0)
+        ev[i + 1].record()
+    barrier()
+    t1 = time.perf_counter()
+    total_ms = ev[0].elapsed_time(ev[K])
+    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
+    st = eng.read_state()
+    assert st.n_centers == K + W, "steps were skipped: %d != %d" % (st.n_centers, K + W)
+    clk = clocks.stop(t0, t1) if rank == 0 else None
+
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms = float(tmax.cpu()[0])
+    value = n_total * K / (total_ms * 1e-3)
+
+    # roofline of the dominant kernel (the fused step): algorithmic bytes per launch
+    # = (12*A + 8) bytes per frame x frames per launch, over the mean per-launch
+    # event time on the launching stream
+    peak, peak_src = measured_peaks()
+    bytes_per_launch = (12 * A + 8) * n_local
+    mean_launch_s = float(np.mean(per_launch_ms)) * 1e-3
+    achieved = bytes_per_launch / mean_launch_s / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "kernel": "k_kcenters_step_rmsd<exact=%d>" % int(exact),
+                "bytes_per_launch_algorithmic": bytes_per_launch,
+                "mean_launch_ms": mean_launch_s * 1e3}
+    ncu_traffic = os.path.join(ROOT, "profiles", "traffic_per_launch.json")
+    if os.path.exists(ncu_traffic):
+        try:
+            with open(ncu_traffic) as fh:
+                tr = json.load(fh)
+            if tr.get("n_frames") == n_local and tr.get("n_atoms") == A:
+                roofline["traffic"] = tr.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- `e2e`: public API on a HOST array ---------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        from enspara_b200.cluster import KCenters
+        del eng
+        host = torch.empty((n_local, A, 3), dtype=torch.float32).pin_memory()
+        base = synth.base_conformers(A, 64, 0)
+        chunk = 125_000
+        for lo in range(0, n_local, chunk):
+            m = min(chunk, n_local - lo)
+            host[lo:lo + m].copy_(synth.device_trajectory_aos(
+                m, A, 0, rank * n_local + lo, base=base))
+        torch.cuda.synchronize()
+        del data
+        torch.cuda.empty_cache()
+        host_np = host.numpy()
+        K2 = K
+        est = KCenters("rmsd", n_clusters=K2, mpi_mode=(world > 1))
+        # warm-up of the API path on a small slice (allocator, lazy init), untimed
+        KCenters("rmsd", n_clusters=3, mpi_mode=(world > 1)).fit(host_np[:20000])
+        barrier()
+        t = time.perf_counter()
+        est.fit(host_np)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t
+        tm = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dt = float(tm.cpu()[0])
+        assert len(est.result_.center_indices) == K2
+        e2e = {"value": n_total * K2 / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(n_local * A * 12 / K2),
+               "d2h_bytes_per_step": int(n_local * (4 + 4) / K2),
+               "seconds": dt, "steps": K2,
+               "what": "KCenters('rmsd', n_clusters=%d).fit(pinned host (n,%d,3) float32): "
+                       "H2D + centring + %d iterations + D2H of assignments/distances, per "
+                       "rank on its shard" % (K2, A, K2)}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            _, cpu, _, _ = cpu_kcenters_rate(A, None, 1, args.cpu_seconds)
+        except Exception as exc:  # the oracle is optional for the GPU arm
+            cpu = {"error": repr(exc)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 accumulate / f32 in-out" if exact else "f32 blocks + f64 sums",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_gpu": n_local, "n_atoms": A,
+                       "frames_total": n_total, "l2": "inputs (%.1f GB per GPU) larger than L2; "
+                       "no flush needed" % (n_local * A * 12 / 1e9),
+                       "parallelism": "frames sharded contiguously, 1 all-gather of candidate "
+                                      "records per step" if world > 1 else "single GPU"},
+            "roofline": roofline, "clocks": clk, "gpu_launches": K,
+            "e2e": e2e, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -65,9 +65,7 @@ SIGNATURES = {
 }
 
 #: declared under ``#ifdef EB_PLANNED`` in the header; not yet exported by the library
-PLANNED = {
-    "eb_synth_trajectory_aos", "eb_synth_features",
-}
+PLANNED = set()
 
 _lib = None
 

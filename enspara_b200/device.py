@@ -56,7 +56,7 @@ class DeviceTrajectory:
     """Pre-centred SoA frames + traces in HBM."""
 
     #: frames converted per staging chunk when uploading from the host
-    CHUNK_BYTES = 1 << 30
+    CHUNK_BYTES = 1 << 28
 
     def __init__(self, xyz_soa, traces, n_atoms, topology=None, host=None):
         self.xyz = xyz_soa          # float32 (n, 3, A_pad)
@@ -96,12 +96,32 @@ class DeviceTrajectory:
         out.host = traj
         if n == 0:
             return out
-        per = max(1, cls.CHUNK_BYTES // (12 * A))
-        stage = torch.empty((min(per, n), A, 3), dtype=torch.float32, device=out.xyz.device)
-        for lo in range(0, n, per):
+        # double-buffered upload: the H2D copy of chunk i+1 (copy stream) overlaps the
+        # centring/transposition of chunk i (current stream); truly asynchronous when the
+        # caller's array is pinned, still correct when it is pageable
+        per = max(1, min(n, cls.CHUNK_BYTES // (12 * A)))
+        dev = out.xyz.device
+        src = torch.from_numpy(xyz)
+        cur = torch.cuda.current_stream()
+        copy_stream = torch.cuda.Stream(device=dev)
+        stages = [torch.empty((per, A, 3), dtype=torch.float32, device=dev) for _ in range(2)]
+        for st in stages:
+            st.record_stream(copy_stream)
+        free_ev = [None, None]
+        copy_stream.wait_stream(cur)
+        for ci, lo in enumerate(range(0, n, per)):
             hi = min(n, lo + per)
-            _h2d(xyz[lo:hi], stage[:hi - lo])
-            out.ingest_aos(stage[:hi - lo], lo, precentered)
+            sidx = ci & 1
+            with torch.cuda.stream(copy_stream):
+                if free_ev[sidx] is not None:
+                    copy_stream.wait_event(free_ev[sidx])
+                stages[sidx][:hi - lo].copy_(src[lo:hi], non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(copy_stream)
+            cur.wait_event(ready)
+            out.ingest_aos(stages[sidx][:hi - lo], lo, precentered)
+            free_ev[sidx] = torch.cuda.Event()
+            free_ev[sidx].record(cur)
         return out
 
     def ingest_aos(self, aos_dev, first_frame, precentered=False):

@@ -114,3 +114,53 @@ def features(n, n_features, seed=0, first_row=0):
     r = np.arange(first_row, first_row + n, dtype=np.uint64)[:, None]
     j = np.arange(n_features, dtype=np.uint64)[None, :]
     return u01(seed, STREAM_FEAT, r, j)
+
+
+# ---------------------------------------------------------------------------------------------
+# device-side generation (csrc/eb_synth.cu): same values, written straight into HBM
+# ---------------------------------------------------------------------------------------------
+def device_trajectory_aos(n, n_atoms, seed=0, first_frame=0, n_base=64, base=None):
+    """(n, n_atoms, 3) float32 CUDA tensor, bit-identical to ``trajectory(...)``."""
+    import ctypes
+
+    import torch
+
+    from . import _lib
+    from .device import cuda_device, ptr, stream_ptr
+    if base is None:
+        base = base_conformers(n_atoms, n_base, seed)
+    dev = cuda_device()
+    base_dev = torch.from_numpy(np.ascontiguousarray(base)).to(dev)
+    out = torch.empty((n, n_atoms, 3), dtype=torch.float32, device=dev)
+    _lib.call("eb_synth_trajectory_aos", ptr(out), int(n), int(n_atoms), int(first_frame),
+              ctypes.c_uint64(int(seed)), ptr(base_dev), int(base.shape[0]), stream_ptr())
+    return out
+
+
+def device_trajectory(n, n_atoms, seed=0, first_frame=0, n_base=64, chunk_frames=None):
+    """A ``DeviceTrajectory`` (centred SoA + traces) of synthetic frames generated in HBM chunk
+    by chunk; the raw AoS frames only ever exist for one chunk at a time."""
+    from .device import DeviceTrajectory
+    base = base_conformers(n_atoms, n_base, seed)
+    out = DeviceTrajectory.empty(n, n_atoms)
+    if chunk_frames is None:
+        chunk_frames = max(1, (1 << 29) // (12 * n_atoms))
+    for lo in range(0, n, chunk_frames):
+        m = min(chunk_frames, n - lo)
+        aos = device_trajectory_aos(m, n_atoms, seed, first_frame + lo, base=base)
+        out.ingest_aos(aos, lo)
+    return out
+
+
+def device_features(n, n_features, seed=0, first_row=0):
+    """(n, n_features) float32 ``DeviceFeatures``, bit-identical to ``features(...)``."""
+    import ctypes
+
+    import torch
+
+    from . import _lib
+    from .device import DeviceFeatures, cuda_device, ptr, stream_ptr
+    X = torch.empty((n, n_features), dtype=torch.float32, device=cuda_device())
+    _lib.call("eb_synth_features", ptr(X), int(n), int(n_features), int(first_row),
+              ctypes.c_uint64(int(seed)), stream_ptr())
+    return DeviceFeatures(X)

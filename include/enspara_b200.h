@@ -179,7 +179,6 @@ int eb_count_members(const int32_t *assign, int64_t n, int32_t k, int64_t *count
 int eb_select_member(const int32_t *assign, int64_t n, int32_t cid, int64_t kth, int64_t *out,
                      void *scratch, void *stream);
 
-#ifdef EB_PLANNED /* declared ahead of their implementation; not exported yet */
 /* ---- synthetic data: counter-based generator keyed on (seed, global frame) -
  * Writes centred SoA frames + traces directly in HBM so a 10M x 500-atom trajectory never has
  * to exist on the host.  The same generator is restated in numpy (enspara_b200/synth.py) for
@@ -189,8 +188,6 @@ int eb_synth_trajectory_aos(float *xyz_aos, int64_t n, int n_atoms, int64_t firs
                             void *stream);
 int eb_synth_features(float *X, int64_t n, int64_t n_features, int64_t first_row, uint64_t seed,
                       void *stream);
-
-#endif /* EB_PLANNED */
 
 #ifdef __cplusplus
 }
