@@ -109,7 +109,7 @@ __device__ __forceinline__ void acc_atom(double m[9], float fx, float fy, float 
 // One frame against the staged centre, computed by the 8 lanes l8 = 0..7 of a group.
 // EXACT: every product goes through the float64 pipe.
 // !EXACT: 4-atom float32 FMA blocks per lane, block sums added in float64 (fast mode).
-template <bool EXACT>
+template <bool EXACT, int LDVAR = 0>
 __device__ __forceinline__ void frame_inner_products(double m[9], const float *frame, int A4,
                                                      int l8, const CenterSmem &c)
 {
@@ -118,9 +118,9 @@ __device__ __forceinline__ void frame_inner_products(double m[9], const float *f
     const float4 *pz = py + A4;
 #pragma unroll 2
     for (int j = l8; j < A4; j += 8) {
-        const float4 x = ldg_stream(px + j);
-        const float4 y = ldg_stream(py + j);
-        const float4 z = ldg_stream(pz + j);
+        const float4 x = LDVAR == 1 ? ldg_stream_256(px + j) : ldg_stream(px + j);
+        const float4 y = LDVAR == 1 ? ldg_stream_256(py + j) : ldg_stream(py + j);
+        const float4 z = LDVAR == 1 ? ldg_stream_256(pz + j) : ldg_stream(pz + j);
         const double2 cxl = c.lo[0][j], cxh = c.hi[0][j];
         const double2 cyl = c.lo[1][j], cyh = c.hi[1][j];
         const double2 czl = c.lo[2][j], czh = c.hi[2][j];

@@ -15,6 +15,8 @@
 // the Newton iterations run on full warps and the dist/assign update is a coalesced 128-byte
 // read-modify-write.  The shard arg-max (first occurrence) is folded into the same launch
 // through a last-block reduction that also publishes the candidate record for the next step.
+#include <stdlib.h>
+
 #include "eb_rmsd.cuh"
 
 namespace eb {
@@ -135,7 +137,7 @@ struct StepSmem {
     int64_t center_index;
 };
 
-template <bool EXACT, int MODE>
+template <bool EXACT, int MODE, int VAR>
 __global__ void __launch_bounds__(kStepThreads, 2)
 k_kcenters_step_rmsd(const float *__restrict__ xyz, const double *__restrict__ traces, long n,
                      int A, int A_pad, long frame_offset, const unsigned char *cand_in,
@@ -203,8 +205,19 @@ k_kcenters_step_rmsd(const float *__restrict__ xyz, const double *__restrict__ t
             for (int s = 0; s < 8; ++s) {
                 const long f = base + 4 * s + g;
                 double m[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                if (VAR == 2) {
+                    // software prefetch of the frame this group streams in the next round
+                    // (or the first round of the warp's next chunk) into L2
+                    const long fn = (s < 7) ? f + 4 : ((chunk + warps_total) << 5) + g;
+                    if (fn < n) {
+                        const char *pn = reinterpret_cast<const char *>(xyz + (size_t)fn * 3 * A_pad);
+                        const int n_lines = (12 * A_pad + 127) >> 7;
+                        for (int l = l8; l < n_lines; l += 8) prefetch_l2(pn + ((size_t)l << 7));
+                    }
+                }
                 if (f < n)
-                    frame_inner_products<EXACT>(m, xyz + (size_t)f * 3 * A_pad, A4, l8, cs);
+                    frame_inner_products<EXACT, (VAR == 1 ? 1 : 0)>(
+                        m, xyz + (size_t)f * 3 * A_pad, A4, l8, cs);
                 group8_reduce(m);
                 if (l8 == 0) {
                     double *dst = my_sums + (4 * s + g) * kSumStride;
@@ -295,8 +308,19 @@ static int step_grid(long n)
     return (int)blocks;
 }
 
-template <bool EXACT, int MODE>
-static int launch_step(const float *xyz, const double *traces, long n, int A, long frame_offset,
+static int k1_variant()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("EB_K1_VARIANT");  // developer A/B switch, see DESIGN.md
+        v = e ? atoi(e) : 0;
+        if (v < 0 || v > 2) v = 0;
+    }
+    return v;
+}
+
+template <bool EXACT, int MODE, int VAR>
+static int launch_step_v(const float *xyz, const double *traces, long n, int A, long frame_offset,
                        const void *cand_in, int n_cand, float *dist, int *assign,
                        int n_clusters_limit, double cutoff, eb_kc_state *state,
                        int64_t *center_list, void *partials, void *cand_out,
@@ -308,7 +332,7 @@ static int launch_step(const float *xyz, const double *traces, long n, int A, lo
     if (smem > 227 * 1024)
         return fail(EB_ERR_LIMIT, "%s: n_atoms=%ld needs %ld bytes of shared memory (max 232448)",
                     "rmsd step", (long)A, (long)smem);
-    auto kern = k_kcenters_step_rmsd<EXACT, MODE>;
+    auto kern = k_kcenters_step_rmsd<EXACT, MODE, VAR>;
     static thread_local size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -322,6 +346,16 @@ static int launch_step(const float *xyz, const double *traces, long n, int A, lo
         (unsigned char *)cand_out, center_direct, center_trace_direct, out_only);
     EB_LAUNCH_CHECK();
     return EB_OK;
+}
+
+template <bool EXACT, int MODE, typename... Args> static int launch_step(Args... args)
+{
+    if (MODE == kModeSeed) return launch_step_v<EXACT, MODE, 0>(args...);
+    switch (k1_variant()) {
+        case 1: return launch_step_v<EXACT, MODE, 1>(args...);
+        case 2: return launch_step_v<EXACT, MODE, 2>(args...);
+    }
+    return launch_step_v<EXACT, MODE, 0>(args...);
 }
 
 }  // namespace eb

@@ -38,6 +38,9 @@ def run(n, A, k, exact):
 
 
 if __name__ == "__main__":
-    for (n, A) in ((1250000, 500), (20000, 264), (1000000, 100)):
+    print("EB_K1_VARIANT=%s" % os.environ.get("EB_K1_VARIANT", "0"))
+    sizes = ((1250000, 500), (1250000, 264), (1000000, 100)) if len(sys.argv) < 2 else \
+        [tuple(int(v) for v in a.split("x")) for a in sys.argv[1:]]
+    for (n, A) in sizes:
         for exact in (True, False):
             run(n, A, 50, exact)

@@ -1,0 +1,63 @@
+"""Worker for the multi-rank GPU test (launched by torchrun, one process per GPU):
+sharded k-centers / k-hybrid must equal the single-GPU run bit for bit (contiguous shards keep
+the serial lowest-index tie rule)."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from enspara_b200 import mpi, synth
+    from enspara_b200.cluster import hybrid, kcenters
+    mpi.init_from_env("nccl")
+    rank, size = mpi.rank(), mpi.size()
+    ok = True
+    for (n, A, kw) in ((3001, 50, dict(n_clusters=25)), (2000, 264, dict(dist_cutoff=1.9)),
+                       (5, 10, dict(n_clusters=4))):
+        X = synth.trajectory(n, A, seed=7)
+        bounds = np.linspace(0, n, size + 1).astype(int)
+        mine = X[bounds[rank]:bounds[rank + 1]]
+        serial = kcenters.kcenters(X, "rmsd", mpi_mode=False, **kw)
+        shard = kcenters.kcenters(mine, "rmsd", mpi_mode=True, **kw)
+        glob = [int(bounds[r] + l) for r, l in shard.center_indices]
+        ok &= glob == [int(c) for c in serial.center_indices]
+        ok &= np.array_equal(shard.assignments, serial.assignments[bounds[rank]:bounds[rank + 1]])
+        ok &= np.array_equal(shard.distances, serial.distances[bounds[rank]:bounds[rank + 1]])
+        ok &= len(shard.centers) == len(serial.centers)
+        for a, b in zip(shard.centers, serial.centers):
+            ok &= np.array_equal(np.asarray(a).reshape(-1), np.asarray(b).reshape(-1))
+    # features, euclidean, exact
+    F = synth.features(10007, 16, seed=3)
+    bounds = np.linspace(0, len(F), size + 1).astype(int)
+    serial = kcenters.kcenters(F, "euclidean", n_clusters=30)
+    shard = kcenters.kcenters(F[bounds[rank]:bounds[rank + 1]], "euclidean", n_clusters=30,
+                              mpi_mode=True)
+    ok &= [int(bounds[r] + l) for r, l in shard.center_indices] == \
+        [int(c) for c in serial.center_indices]
+    ok &= np.array_equal(shard.distances, serial.distances[bounds[rank]:bounds[rank + 1]])
+    # k-hybrid: sharded PAM == serial PAM (same seeded RandomState on every rank)
+    X = synth.trajectory(1200, 30, seed=11)
+    bounds = np.linspace(0, len(X), size + 1).astype(int)
+    serial = hybrid.hybrid(X, "rmsd", n_clusters=8, n_iters=2, random_state=0)
+    shard = hybrid.hybrid(X[bounds[rank]:bounds[rank + 1]], "rmsd", n_clusters=8, n_iters=2,
+                          random_state=0, mpi_mode=True)
+    ok &= [int(bounds[r] + l) for r, l in shard.center_indices] == \
+        [int(c) for c in serial.center_indices]
+    ok &= np.array_equal(shard.assignments, serial.assignments[bounds[rank]:bounds[rank + 1]])
+    ok &= np.array_equal(shard.distances, serial.distances[bounds[rank]:bounds[rank + 1]])
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("MGPU_OK" if int(flag.item()) == 1 else "MGPU_FAIL", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

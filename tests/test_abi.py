@@ -45,8 +45,9 @@ def test_library_loads_and_layout_helpers_work_without_gpu():
     from enspara_b200 import _lib
     L = _lib.load()
     assert L.eb_version() >= 100
-    assert L.eb_rmsd_apad(500) == 504 and L.eb_rmsd_apad(264) == 264 and L.eb_rmsd_apad(22) == 24
-    assert L.eb_rmsd_record_bytes(500) == 32 + 12 * 504
+    assert L.eb_rmsd_apad(500) == 512 and L.eb_rmsd_apad(264) == 264 and L.eb_rmsd_apad(22) == 24
+    assert L.eb_rmsd_apad(1000) == 1024 and L.eb_rmsd_apad(33) == 40
+    assert L.eb_rmsd_record_bytes(500) == 32 + 12 * 512
     assert L.eb_feat_record_bytes(64, _lib.DT_F32) == 32 + 256
     assert L.eb_feat_record_bytes(3, _lib.DT_I8) == 32 + 16
     assert L.eb_kc_partials_bytes() >= 16 * 1024
