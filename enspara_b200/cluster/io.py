@@ -1,0 +1,172 @@
+"""Loading inputs and writing outputs for the `cluster` app -- the callers either side of the
+hot path.  Behaviour follows the reference's
+/root/reference/enspara/cluster/util.py:315-549 and mpi/io.py:16-194; mdtraj (trajectory
+files) and PyTables (.h5) are imported lazily and only needed for those formats, as in the
+reference.  `.npy` feature files need neither.
+"""
+import logging
+import os
+import pickle
+from glob import glob
+
+import numpy as np
+
+from .. import mpi, ra
+from ..exception import ImproperlyConfigured
+
+logger = logging.getLogger(__name__)
+
+
+def expand_files(pgroups):
+    """Glob-expand groups of path patterns (util.py:315-321)."""
+    out = []
+    for pgroup in pgroups:
+        out.append([])
+        for p in pgroup:
+            out[-1].extend(sorted(glob(p)))
+    return out
+
+
+def load_npy_as_striped(filenames, stride=1):
+    """File i is loaded by rank i % size (mpi/io.py:68-139).  Returns (global lengths, local
+    concatenated array)."""
+    specs = [(h.shape, h.dtype) for h in (np.load(f, mmap_mode="r") for f in filenames)]
+    shape0, dtype = specs[0]
+    for i, (s, d) in enumerate(specs):
+        if s[1:] != shape0[1:]:
+            raise ImproperlyConfigured(
+                "Subsequent dimensions of file '{}' didn't match shape of first file, '{}' "
+                "({} != {})".format(filenames[0], filenames[i], shape0, s))
+        if d != dtype:
+            raise ImproperlyConfigured(
+                "Type of file '{}' didn't match type first file, '{}' ({} != {})".format(
+                    filenames[0], filenames[i], dtype, d))
+    if len(filenames) < mpi.size():
+        raise ImproperlyConfigured(
+            "To stripe files across workers, at least 1 file per rank must be given. "
+            "World size is %s, number of files is %s." % (mpi.size(), len(filenames)))
+    global_lengths = [len(range(0, s[0], stride)) for s, _ in specs]
+    local = [np.load(f, mmap_mode="r")[::stride] for f in filenames[mpi.rank()::mpi.size()]]
+    data = np.concatenate(local) if local else np.empty((0,) + shape0[1:], dtype=dtype)
+    return global_lengths, np.ascontiguousarray(data)
+
+
+def load_h5_as_striped(filename, stride=1):
+    """Rows of a RaggedArray .h5 striped over ranks (mpi/io.py:16-65); needs PyTables."""
+    try:
+        import tables  # noqa: F401
+    except ImportError:
+        raise ImproperlyConfigured(
+            "Reading '%s' needs PyTables, which is not installed; pass several .npy files "
+            "to --features instead." % filename)
+    arr = ra.load(filename)
+    rows = [np.asarray(arr[i])[::stride] for i in range(len(arr))]
+    global_lengths = [len(r) for r in rows]
+    mine = rows[mpi.rank()::mpi.size()]
+    return global_lengths, np.ascontiguousarray(np.concatenate(mine))
+
+
+def load_features(features, stride):
+    if len(features) == 1 and os.path.splitext(features[0])[1].lower() in (".h5", ".hdf5"):
+        lengths, data = load_h5_as_striped(features[0], stride)
+    else:
+        lengths, data = load_npy_as_striped(features, stride)
+    logger.info("Loaded %s trajectories with %s frames with stride %s.", len(lengths),
+                len(data), stride)
+    return lengths, data
+
+
+def load_trajectories(topologies, trajectories, selections, stride):
+    """Trajectory files -> (global lengths, md.Trajectory of this rank's frames); file i of the
+    flattened list goes to rank i % size (util.py:350-404, mpi/io.py:142-194).  Needs mdtraj."""
+    try:
+        import mdtraj as md
+    except ImportError:
+        raise ImproperlyConfigured(
+            "Loading trajectory files needs mdtraj, which is not installed.")
+    flat, tops, inds, n_inds, top = [], [], [], None, None
+    for topfile, trjset, selection in zip(topologies, trajectories, selections):
+        top = md.load(topfile).top
+        try:
+            indices = top.select(selection)
+        except Exception:
+            raise ImproperlyConfigured(
+                "The provided selection '{s}' didn't match the topology file, {t}".format(
+                    s=selection, t=topfile))
+        if n_inds is not None and n_inds != len(indices):
+            raise ImproperlyConfigured(
+                "Selection on topology %s selected %s atoms, but other selections selected "
+                "%s atoms." % (topfile, len(indices), n_inds))
+        n_inds = len(indices)
+        for trj in trjset:
+            flat.append(trj)
+            tops.append(top)
+            inds.append(indices)
+    if len(flat) < mpi.size():
+        raise ImproperlyConfigured(
+            "To stripe files across workers, at least 1 file per rank must be given.")
+    mine = range(mpi.rank(), len(flat), mpi.size())
+    loaded = [md.load(flat[i], top=tops[i], stride=stride, atom_indices=inds[i]) for i in mine]
+    local_lengths = np.array([len(t) for t in loaded], dtype=int)
+    lengths = mpi.ops.assemble_striped_array(local_lengths)
+    xyz = np.concatenate([t.xyz for t in loaded])
+    sel_top = top.subset(top.select(selections[-1]))
+    return lengths, md.Trajectory(xyz=xyz, topology=sel_top)
+
+
+def load_trjs_or_features(args):
+    if args.features:
+        return load_features(args.features, stride=args.subsample)
+    return load_trajectories(args.topologies, args.trajectories, args.atoms, args.subsample)
+
+
+def _intermediate_path(path, tag):
+    d = os.path.join(os.path.dirname(path), "intermediate-%s" % tag)
+    os.makedirs(d, exist_ok=True)
+    return os.path.join(d, os.path.basename(path))
+
+
+def write_centers_indices(path, indices, intermediate_n=None):
+    """(trajectory, frame) pairs as .npy (util.py:464-478)."""
+    if not path:
+        logger.info("--center-indices not provided, not writing center indices to file.")
+        return
+    if intermediate_n is not None:
+        path = _intermediate_path(path, intermediate_n)
+    with open(path, "wb") as f:
+        np.save(f, indices)
+
+
+def write_centers(result, args, intermediate_n=None):
+    """Feature centres -> .npy; trajectory centres -> pickle of frames (util.py:481-508)."""
+    path = args.center_features
+    if intermediate_n is not None:
+        path = _intermediate_path(path, intermediate_n)
+    if args.features:
+        np.save(path, np.asarray(result.centers))
+    else:
+        with open(path, "wb") as f:
+            pickle.dump(result.centers, f)
+
+
+def write_assignments_and_distances(result, args, intermediate_n=None):
+    """util.py:511-549 for subsample == 1 (re-assignment of skipped frames is the `reassign`
+    app's job)."""
+    dpath, apath = args.distances, args.assignments
+    if intermediate_n is not None:
+        dpath = _intermediate_path(dpath, intermediate_n)
+        apath = _intermediate_path(apath, intermediate_n)
+    ra.save(dpath, result.distances)
+    ra.save(apath, result.assignments)
+
+
+def write_intermediate(result, args, lengths, tag):
+    """--save_intermediates dumps (hybrid.py:129-151, kmedoids.py:459-473)."""
+    if mpi.size() > 1:
+        return  # intermediates are written from assembled results only in serial runs
+    part = result.partition(lengths)
+    write_centers_indices(args.center_indices,
+                          [(t, f * args.subsample) for t, f in part.center_indices],
+                          intermediate_n=tag)
+    write_centers(part, args, intermediate_n=tag)
+    write_assignments_and_distances(part, args, intermediate_n=tag)

@@ -84,3 +84,75 @@ def partition_indices(indices, traj_lengths):
         if 0 <= t < len(traj_lengths):
             out.append((t, index - int(bounds[t])))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# save / load.  The reference writes one zlib CArray ``arr_<i>`` per trajectory with PyTables
+# (ra.py:45-89) and needs PyTables to read them back.  PyTables is optional here: `.h5` paths
+# use it when importable, `.npy` / `.npz` paths work everywhere.
+# ---------------------------------------------------------------------------------------------
+def _rows(obj):
+    if isinstance(obj, RaggedArray):
+        return [obj[i] for i in range(len(obj))], False
+    arr = np.asarray(obj)
+    if arr.ndim >= 2:
+        return [arr[i] for i in range(arr.shape[0])], True
+    return [arr], True
+
+
+def save(path, obj):
+    """Write a (ragged) array.  `.h5`: PyTables layout of the reference; `.npy`: dense array
+    (rows of equal length only); `.npz`: flat data + lengths."""
+    import os
+    ext = os.path.splitext(path)[1].lower()
+    rows, square = _rows(obj)
+    if ext in (".h5", ".hdf5"):
+        try:
+            import tables
+        except ImportError:
+            from .exception import ImproperlyConfigured
+            raise ImproperlyConfigured(
+                "Writing '%s' needs PyTables (as in the reference); it is not installed. "
+                "Use a .npy / .npz path instead." % path)
+        compression = tables.Filters(complevel=9, complib="zlib", shuffle=True)
+        with tables.open_file(path, mode="w") as handle:
+            if square and not isinstance(obj, RaggedArray):
+                arr = np.asarray(obj)
+                atom = tables.Atom.from_dtype(arr.dtype)
+                node = handle.create_carray(where="/", name="array", atom=atom,
+                                            shape=arr.shape, filters=compression)
+                node[:] = arr
+            else:
+                n_zeros = len(str(len(rows))) + 1
+                for i, row in enumerate(rows):
+                    row = np.asarray(row)
+                    atom = tables.Atom.from_dtype(row.dtype)
+                    node = handle.create_carray(
+                        where="/", name="array_" + str(i).zfill(n_zeros), atom=atom,
+                        shape=row.shape, filters=compression)
+                    node[:] = row
+        return
+    if ext == ".npz" or not square or isinstance(obj, RaggedArray):
+        flat = np.concatenate([np.asarray(r).reshape(-1) for r in rows]) if rows else np.zeros(0)
+        np.savez(path if ext == ".npz" else path + ".npz", data=flat,
+                 lengths=np.array([len(r) for r in rows], dtype=np.int64))
+        return
+    np.save(path, np.asarray(obj))
+
+
+def load(path):
+    """Inverse of ``save`` for the .npy / .npz forms (and .h5 when PyTables is present)."""
+    import os
+    ext = os.path.splitext(path)[1].lower()
+    if ext in (".h5", ".hdf5"):
+        import tables
+        with tables.open_file(path) as handle:
+            names = sorted(n.name for n in handle.list_nodes("/"))
+            if names == ["array"]:
+                return handle.get_node("/array")[:]
+            rows = [handle.get_node("/" + n)[:] for n in names]
+        return RaggedArray(rows)
+    if ext == ".npz":
+        z = np.load(path)
+        return RaggedArray(z["data"], lengths=z["lengths"])
+    return np.load(path)
