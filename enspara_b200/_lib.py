@@ -42,12 +42,12 @@ SIGNATURES = {
     "eb_soa_to_aos": (_int, [_vp, _i64, _int, _vp, _vp]),
     "eb_gather_frames": (_int, [_vp, _vp, _int, _vp, _i64, _vp, _vp, _vp]),
     "eb_kcenters_step_rmsd": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _int, _vp, _vp, _i32,
-                                     _dbl, _vp, _vp, _vp, _vp, _int, _vp]),
+                                     _dbl, _vp, _vp, _vp, _vp, _int, _int, _vp]),
     "eb_kcenters_seed_rmsd": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _i32, _vp, _vp, _vp,
                                      _vp]),
     "eb_rmsd_one_to_all": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _vp, _int, _vp]),
     "eb_kcenters_step_feat": (_int, [_vp, _i64, _i64, _int, _int, _i64, _vp, _int, _vp, _vp,
-                                     _i32, _dbl, _vp, _vp, _vp, _vp, _vp]),
+                                     _i32, _dbl, _vp, _vp, _vp, _vp, _int, _vp]),
     "eb_kcenters_seed_feat": (_int, [_vp, _i64, _i64, _int, _i64, _vp, _i32, _vp, _vp, _vp,
                                      _vp]),
     "eb_feat_one_to_all": (_int, [_vp, _i64, _i64, _int, _int, _vp, _vp, _vp]),

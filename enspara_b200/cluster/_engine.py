@@ -105,7 +105,13 @@ class KCentersEngine:
         self.launches += 1
         self._exchange()
 
-    def step(self, n_clusters_limit, cutoff):
+    def step(self, n_clusters_limit, cutoff, n_steps=1):
+        """Queue ``n_steps`` iterations.  A single shard queues them inside one C call (no
+        Python per launch); sharded runs interleave the candidate all-gather."""
+        if self.shard.size > 1 and n_steps > 1:
+            for _ in range(n_steps):
+                self.step(n_clusters_limit, cutoff, 1)
+            return
         s = stream_ptr()
         d = self.data
         if self.is_rmsd:
@@ -113,14 +119,14 @@ class KCentersEngine:
                       self.shard.offset, ptr(self.cand_all), self.shard.size, ptr(self.dist),
                       ptr(self.assign), n_clusters_limit, float(cutoff), ptr(self.state),
                       ptr(self.center_list), ptr(self.partials), ptr(self.cand_out),
-                      int(self.exact), s)
+                      int(self.exact), int(n_steps), s)
         else:
             _lib.call("eb_kcenters_step_feat", ptr(d.X), self.n, d.n_features, d.dt,
                       _lib_metric(self.kind), self.shard.offset, ptr(self.cand_all),
                       self.shard.size, ptr(self.dist), ptr(self.assign), n_clusters_limit,
                       float(cutoff), ptr(self.state), ptr(self.center_list),
-                      ptr(self.partials), ptr(self.cand_out), s)
-        self.launches += 1
+                      ptr(self.partials), ptr(self.cand_out), int(n_steps), s)
+        self.launches += n_steps
         self._exchange()
 
     def _ensure_center_list(self, capacity):
@@ -160,8 +166,8 @@ class KCentersEngine:
                 self._ensure_center_list(min(hard_cap, max(2 * self.center_list.numel(),
                                                            queued + batch)))
                 batch = min(batch, self.center_list.numel() - queued)
-            for _ in range(batch):
-                self.step(limit, cutoff)
+            if batch > 0:
+                self.step(limit, cutoff, batch)
             queued += batch
             st = self.read_state()
             if on_progress is not None:

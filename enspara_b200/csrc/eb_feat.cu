@@ -15,11 +15,11 @@
 // tile of 32 rows x 256 bytes into shared memory with 16-byte vector loads (two rows per
 // request), padded so the per-lane 16-byte reads are bank-conflict free.  HBM bound: each row
 // byte is read once; dist (float64) is a coalesced read-modify-write.
-#include "eb_common.cuh"
+#include "eb_tma.cuh"
 
 namespace eb {
 
-constexpr int kFeatThreads = 256;
+constexpr int kFeatThreads = 128;
 constexpr int kFeatWarps = kFeatThreads / 32;
 constexpr int kTileBytes = 256;                 // bytes of one row held per tile
 constexpr int kTileStride = kTileBytes + 16;    // 17 x 16 B: odd -> conflict-free LDS.128
@@ -119,6 +119,59 @@ __device__ __forceinline__ double warp_rows_distance(const T *__restrict__ X, lo
     return finish<METRIC>(acc);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// TMA staging: a warp's tile (32 rows x 256 bytes) arrives as two 32x128-byte boxes of a 2-D
+// tensor map with the 128-byte hardware swizzle, so lane l can walk ITS row with conflict-free
+// 16-byte reads (chunk c of row r sits at chunk c ^ (r & 7)); one elected lane issues the
+// copies, the LSU never touches the staging traffic, and tile q+1 is in flight while tile q is
+// being walked.
+// ------------------------------------------------------------------------------------------
+constexpr int kBoxBytes = 32 * 128;           // one box: 32 rows x 128 bytes
+constexpr int kTmaTileBytes = 2 * kBoxBytes;  // 256 bytes of each of 32 rows
+
+template <typename T, int METRIC>
+__device__ __forceinline__ double tile_terms_swz(double acc, const unsigned char *tile, int lane,
+                                                 const T *y_sh, long j0, int fe)
+{
+    constexpr int VE = 16 / (int)sizeof(T);
+    const unsigned char *row = tile + lane * 128;
+    const int sw = lane & 7;
+#pragma unroll 4
+    for (int c = 0; c < fe; c += VE) {
+        const int byteoff = c * (int)sizeof(T);
+        const int box = byteoff >> 7, chunk = (byteoff >> 4) & 7;
+        const int4 raw = *reinterpret_cast<const int4 *>(row + box * kBoxBytes +
+                                                         ((chunk ^ sw) << 4));
+        const int4 yraw = *reinterpret_cast<const int4 *>(y_sh + j0 + c);  // broadcast read
+        const T *v = reinterpret_cast<const T *>(&raw);
+        const T *yv = reinterpret_cast<const T *>(&yraw);
+#pragma unroll
+        for (int u = 0; u < VE; ++u) acc = __dadd_rn(acc, Term<T, METRIC>::f(v[u], yv[u]));
+    }
+    return acc;
+}
+
+// one staged tile: add this tile's terms to the lane's running row sum, in feature order
+template <typename T, int METRIC>
+__device__ __forceinline__ double tile_terms(double acc, const unsigned char *tile, int lane,
+                                             const T *y_sh, long j0, int fe)
+{
+    const T *row = reinterpret_cast<const T *>(tile + lane * kTileStride);
+    constexpr int VE = 16 / (int)sizeof(T);
+    int c = 0;
+    for (; c + VE <= fe; c += VE) {
+        const int4 raw = *reinterpret_cast<const int4 *>(row + c);
+        const int4 yraw = *reinterpret_cast<const int4 *>(y_sh + j0 + c);  // broadcast read
+        const T *v = reinterpret_cast<const T *>(&raw);
+        const T *yv = reinterpret_cast<const T *>(&yraw);
+#pragma unroll
+        for (int u = 0; u < VE; ++u) acc = __dadd_rn(acc, Term<T, METRIC>::f(v[u], yv[u]));
+    }
+    for (; c < fe; ++c) acc = __dadd_rn(acc, Term<T, METRIC>::f(row[c], y_sh[j0 + c]));
+    return acc;
+}
+
 enum FeatMode { kFStep = 0, kFSeed = 1, kFDistOnly = 2 };
 
 struct FeatSmem {
@@ -134,15 +187,26 @@ k_kcenters_step_feat(const T *__restrict__ X, long n, long F, long frame_offset,
                      const unsigned char *cand_in, int n_cand, size_t rec_bytes, double *dist,
                      int *assign, int n_clusters_limit, double cutoff, eb_kc_state *state,
                      int64_t *center_list, Partial *partials, unsigned char *cand_out,
-                     const T *y_direct, double *out_only, int vec_ok)
+                     const T *y_direct, double *out_only, int vec_ok,
+                     const __grid_constant__ CUtensorMap tmap)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    FeatSmem *ss = reinterpret_cast<FeatSmem *>(smem_raw);
-    unsigned char *tiles = smem_raw + align16(sizeof(FeatSmem));
-    T *y_sh = reinterpret_cast<T *>(tiles + (size_t)kFeatWarps * 32 * kTileStride);
+    // layout: [per-warp tiles: 2 x 8 KB, 1024-byte aligned for the swizzle] [FeatSmem] [bars] [y]
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *tiles = smem_raw;
+    FeatSmem *ss = reinterpret_cast<FeatSmem *>(tiles + (size_t)kFeatWarps * 2 * kTmaTileBytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(ss) +
+                                                  align16(sizeof(FeatSmem)));
+    T *y_sh = reinterpret_cast<T *>(bars + 2 * kFeatWarps);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int k = 0;
+    if (lane == 0) {
+        mbar_init(bars + 2 * warp, 1);
+        mbar_init(bars + 2 * warp + 1, 1);
+        fence_mbar_init();
+        if (vec_ok) tma_prefetch_desc(&tmap);
+    }
+    __syncwarp();
 
     if (MODE == kFStep) {
         double cd;
@@ -177,15 +241,10 @@ k_kcenters_step_feat(const T *__restrict__ X, long n, long F, long frame_offset,
     int64_t best_i = INT64_MAX;
     const long n_chunks = (n + 31) >> 5;
     const long warps_total = (long)gridDim.x * kFeatWarps;
-    unsigned char *tile = tiles + (size_t)warp * 32 * kTileStride;
+    unsigned char *tile = tiles + (size_t)warp * 2 * kTmaTileBytes;
 
-    for (long chunk = (long)blockIdx.x * kFeatWarps + warp; chunk < n_chunks;
-         chunk += warps_total) {
-        const long base = chunk << 5;
-        const long row = base + lane;
-        double d = 0.0;
-        if (MODE != kFSeed)
-            d = warp_rows_distance<T, METRIC>(X, n, F, base, y_sh, tile, vec_ok != 0);
+    // commit one finished row (strict '<' update, arg-max tracking)
+    auto commit = [&](long row, double d) {
         if (row < n) {
             double cur;
             if (MODE == kFSeed) {
@@ -205,6 +264,65 @@ k_kcenters_step_feat(const T *__restrict__ X, long n, long F, long frame_offset,
                 best_d = cur;
                 best_i = row;
             }
+        }
+    };
+
+    const long first_chunk = (long)blockIdx.x * kFeatWarps + warp;
+    if (MODE != kFSeed && vec_ok) {
+        // ---- pipelined TMA path ------------------------------------------------------------
+        constexpr int EPT = kTileBytes / (int)sizeof(T);   // elements of a row per tile
+        constexpr int EPB = 128 / (int)sizeof(T);          // elements of a row per box
+        const int nt = (int)((F + EPT - 1) / EPT);         // tiles per 32-row chunk
+        uint64_t *bar = bars + 2 * warp;
+        // producer cursor (next tile to request) and consumer cursor (tile being walked)
+        long p_chunk = first_chunk, c_chunk = first_chunk;
+        int p_jt = 0, c_jt = 0, p_buf = 0;
+        auto issue = [&]() {
+            if (lane == 0) {
+                const long j0 = (long)p_jt * EPT;
+                const int fe = (int)min((long)EPT, F - j0);
+                const int n_box = (fe + EPB - 1) / EPB;
+                unsigned char *dst = tile + p_buf * kTmaTileBytes;
+                mbar_expect_tx(bar + p_buf, (uint32_t)n_box * kBoxBytes);
+                for (int b = 0; b < n_box; ++b)
+                    tma_load_2d(dst + b * kBoxBytes, &tmap, (int)(j0 + (long)b * EPB),
+                                (int)(p_chunk << 5), bar + p_buf);
+            }
+            p_buf ^= 1;
+            if (++p_jt == nt) {
+                p_jt = 0;
+                p_chunk += warps_total;
+            }
+        };
+        uint32_t phase0 = 0, phase1 = 0;
+        double acc = 0.0;
+        int c_buf = 0;
+        if (p_chunk < n_chunks) issue();
+        while (c_chunk < n_chunks) {
+            if (p_chunk < n_chunks) issue();
+            mbar_wait(bar + c_buf, c_buf ? phase1 : phase0);
+            if (c_buf) phase1 ^= 1; else phase0 ^= 1;
+            const long j0 = (long)c_jt * EPT;
+            const int fe = (int)min((long)EPT, F - j0);
+            acc = tile_terms_swz<T, METRIC>(acc, tile + c_buf * kTmaTileBytes, lane, y_sh, j0, fe);
+            if (c_jt == nt - 1) {
+                commit((c_chunk << 5) + lane, finish<METRIC>(acc));
+                acc = 0.0;
+            }
+            c_buf ^= 1;
+            if (++c_jt == nt) {
+                c_jt = 0;
+                c_chunk += warps_total;
+            }
+            __syncwarp();  // everyone is done with this buffer before it is refilled
+        }
+    } else {
+        for (long chunk = first_chunk; chunk < n_chunks; chunk += warps_total) {
+            const long base = chunk << 5;
+            double d = 0.0;
+            if (MODE != kFSeed)
+                d = warp_rows_distance<T, METRIC>(X, n, F, base, y_sh, tile, false);
+            commit(base + lane, d);
         }
     }
     if (MODE == kFDistOnly) return;
@@ -251,7 +369,7 @@ k_feat_assign(const T *__restrict__ X, long n, long F, const T *__restrict__ cen
               const int64_t *__restrict__ frame_idx, long m, double *out_dist, int *out_assign,
               int accumulate, int scatter)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *tiles = smem_raw;
     T *y_all = reinterpret_cast<T *>(tiles + (size_t)kFeatWarps * 32 * kTileStride);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -328,6 +446,14 @@ k_feat_assign(const T *__restrict__ X, long n, long F, const T *__restrict__ cen
 // ------------------------------------------------------------------------------------------
 // host-side dispatch
 // ------------------------------------------------------------------------------------------
+template <typename T> static CUtensorMapDataType tmap_dtype();
+template <> CUtensorMapDataType tmap_dtype<float>() { return CU_TENSOR_MAP_DATA_TYPE_FLOAT32; }
+template <> CUtensorMapDataType tmap_dtype<double>() { return CU_TENSOR_MAP_DATA_TYPE_FLOAT64; }
+template <> CUtensorMapDataType tmap_dtype<int8_t>() { return CU_TENSOR_MAP_DATA_TYPE_UINT8; }
+template <> CUtensorMapDataType tmap_dtype<int16_t>() { return CU_TENSOR_MAP_DATA_TYPE_UINT16; }
+template <> CUtensorMapDataType tmap_dtype<int32_t>() { return CU_TENSOR_MAP_DATA_TYPE_INT32; }
+template <> CUtensorMapDataType tmap_dtype<int64_t>() { return CU_TENSOR_MAP_DATA_TYPE_INT64; }
+
 static size_t elem_size(int dtype)
 {
     switch (dtype) {
@@ -343,8 +469,8 @@ static size_t elem_size(int dtype)
 
 static size_t feat_smem(long F, size_t es, int n_y)
 {
-    return align16(sizeof(FeatSmem)) + (size_t)kFeatWarps * 32 * kTileStride +
-           align16((size_t)F * es) * n_y;
+    return (size_t)kFeatWarps * 2 * kTmaTileBytes + align16(sizeof(FeatSmem)) +
+           16 * kFeatWarps + align16((size_t)F * es) * n_y + 1024;
 }
 
 static int feat_grid(long n, size_t smem)
@@ -352,7 +478,7 @@ static int feat_grid(long n, size_t smem)
     const long chunks = (n + 31) / 32;
     long blocks = (chunks + kFeatWarps - 1) / kFeatWarps;
     int per_sm = (int)((220 * 1024) / (smem + 1024));
-    if (per_sm > 4) per_sm = 4;
+    if (per_sm > 6) per_sm = 6;
     if (per_sm < 1) per_sm = 1;
     const long cap = (long)per_sm * sm_count();
     if (blocks > cap) blocks = cap;
@@ -378,11 +504,26 @@ static int launch_feat(const void *X, long n, long F, long frame_offset, const v
         configured = 227 * 1024;
     }
     const size_t rec_bytes = sizeof(RecHeader) + align16((size_t)F * sizeof(T));
-    const int vec_ok = (((size_t)F * sizeof(T)) % 16 == 0) && (((uintptr_t)X) % 16 == 0);
+    int vec_ok = (((size_t)F * sizeof(T)) % 16 == 0) && (((uintptr_t)X) % 16 == 0) &&
+                 MODE != kFSeed && n > 0 && n < (1L << 31) && F < (1L << 31);
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+    if (vec_ok) {
+        const uint32_t box_cols = (uint32_t)min((long)(128 / sizeof(T)), F);
+        // a box narrower than 128 bytes cannot use the 128-byte swizzle: fall back
+        if (box_cols * sizeof(T) != 128) {
+            vec_ok = 0;
+        } else {
+            const int rc = make_tmap_2d(&tmap, X, tmap_dtype<T>(), sizeof(T), (uint64_t)n,
+                                        (uint64_t)F, (uint64_t)F * sizeof(T), 32, box_cols,
+                                        CU_TENSOR_MAP_SWIZZLE_128B);
+            if (rc != EB_OK) return rc;
+        }
+    }
     kern<<<feat_grid(n, smem), kFeatThreads, smem, stream>>>(
         (const T *)X, n, F, frame_offset, (const unsigned char *)cand_in, n_cand, rec_bytes, dist,
         assign, limit, cutoff, state, center_list, (Partial *)partials,
-        (unsigned char *)cand_out, (const T *)y_direct, out_only, vec_ok);
+        (unsigned char *)cand_out, (const T *)y_direct, out_only, vec_ok, tmap);
     EB_LAUNCH_CHECK();
     return EB_OK;
 }
@@ -460,16 +601,24 @@ int eb_kcenters_step_feat(const void *X, int64_t n, int64_t n_features, int dtyp
                           int64_t frame_offset, const void *cand_in, int n_cand, double *dist,
                           int32_t *assign, int32_t n_clusters_limit, double dist_cutoff,
                           eb_kc_state *state, int64_t *center_list, void *partials,
-                          void *cand_out, void *stream)
+                          void *cand_out, int n_steps, void *stream)
 {
     EB_CHECK_ARG(n >= 0 && n_features > 0, "kcenters_step_feat: bad shape");
+    EB_CHECK_ARG(n_steps >= 1, "kcenters_step_feat: n_steps < 1");
+    EB_CHECK_ARG(n_steps == 1 || (n_cand == 1 && cand_in == cand_out),
+                 "kcenters_step_feat: n_steps > 1 needs a single shard (cand_in == cand_out)");
     EB_CHECK_ARG(elem_size(dtype) != 0, "kcenters_step_feat: unknown dtype");
     EB_CHECK_ARG(n_cand >= 1 && cand_in && cand_out && state && partials && center_list,
                  "kcenters_step_feat: null pointer / n_cand < 1");
-    return dispatch<kFStep>(dtype, metric, X, (long)n, (long)n_features, (long)frame_offset,
-                            cand_in, n_cand, dist, assign, (int)n_clusters_limit, dist_cutoff,
-                            state, center_list, partials, cand_out, (const void *)nullptr,
-                            (double *)nullptr, (cudaStream_t)stream);
+    for (int it = 0; it < n_steps; ++it) {
+        const int rc = dispatch<kFStep>(dtype, metric, X, (long)n, (long)n_features,
+                                        (long)frame_offset, cand_in, n_cand, dist, assign,
+                                        (int)n_clusters_limit, dist_cutoff, state, center_list,
+                                        partials, cand_out, (const void *)nullptr,
+                                        (double *)nullptr, (cudaStream_t)stream);
+        if (rc != EB_OK) return rc;
+    }
+    return EB_OK;
 }
 
 int eb_kcenters_seed_feat(const void *X, int64_t n, int64_t n_features, int dtype,

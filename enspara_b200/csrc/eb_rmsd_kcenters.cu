@@ -429,21 +429,30 @@ int eb_kcenters_step_rmsd(const float *xyz_soa, const double *traces, int64_t n,
                           int64_t frame_offset, const void *cand_in, int n_cand, float *dist,
                           int32_t *assign, int32_t n_clusters_limit, double dist_cutoff,
                           eb_kc_state *state, int64_t *center_list, void *partials,
-                          void *cand_out, int exact, void *stream)
+                          void *cand_out, int exact, int n_steps, void *stream)
 {
     EB_CHECK_ARG(n >= 0 && n_atoms > 0, "kcenters_step_rmsd: bad shape");
+    EB_CHECK_ARG(n_steps >= 1, "kcenters_step_rmsd: n_steps < 1");
+    EB_CHECK_ARG(n_steps == 1 || (n_cand == 1 && cand_in == cand_out),
+                 "kcenters_step_rmsd: n_steps > 1 needs a single shard (cand_in == cand_out)");
     EB_CHECK_ARG(n_cand >= 1 && cand_in && cand_out && state && partials && center_list,
                  "kcenters_step_rmsd: null pointer / n_cand < 1");
     EB_CHECK_ARG(n < (int64_t(1) << 40), "kcenters_step_rmsd: shard too large");
-    if (exact)
-        return launch_step<true, kModeStep>(xyz_soa, traces, n, n_atoms, frame_offset, cand_in,
-                                            n_cand, dist, assign, n_clusters_limit, dist_cutoff,
-                                            state, center_list, partials, cand_out, nullptr, nullptr,
-                                            nullptr, (cudaStream_t)stream);
-    return launch_step<false, kModeStep>(xyz_soa, traces, n, n_atoms, frame_offset, cand_in,
-                                         n_cand, dist, assign, n_clusters_limit, dist_cutoff,
-                                         state, center_list, partials, cand_out, nullptr, nullptr,
-                                         nullptr, (cudaStream_t)stream);
+    for (int it = 0; it < n_steps; ++it) {
+        const int rc =
+            exact ? launch_step<true, kModeStep>(xyz_soa, traces, n, n_atoms, frame_offset,
+                                                 cand_in, n_cand, dist, assign, n_clusters_limit,
+                                                 dist_cutoff, state, center_list, partials,
+                                                 cand_out, nullptr, nullptr, nullptr,
+                                                 (cudaStream_t)stream)
+                  : launch_step<false, kModeStep>(xyz_soa, traces, n, n_atoms, frame_offset,
+                                                  cand_in, n_cand, dist, assign, n_clusters_limit,
+                                                  dist_cutoff, state, center_list, partials,
+                                                  cand_out, nullptr, nullptr, nullptr,
+                                                  (cudaStream_t)stream);
+        if (rc != EB_OK) return rc;
+    }
+    return EB_OK;
 }
 
 int eb_kcenters_seed_rmsd(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,

@@ -107,12 +107,14 @@ int eb_gather_frames(const float *xyz_soa, const double *traces, int n_atoms,
  * cand_in may alias cand_out (single GPU).  dist is float32 (values are float32 in the
  * reference too: md.rmsd returns float32), assign int32; the host layer widens them to the
  * reference's float64 / int64 when it copies results out.  exact=1 accumulates the matrix in
- * float64 (parity mode, default); exact=0 uses float32 blocks of 8 atoms + float64 block sums. */
+ * float64 (parity mode, default); exact=0 uses float32 blocks of 4 atoms + float64 block sums.
+ * n_steps > 1 queues that many consecutive iterations in one call (single shard only: the
+ * next step reads the record this one wrote; sharded runs interleave the all-gather). */
 int eb_kcenters_step_rmsd(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
                           int64_t frame_offset, const void *cand_in, int n_cand,
                           float *dist, int32_t *assign, int32_t n_clusters_limit,
                           double dist_cutoff, eb_kc_state *state, int64_t *center_list,
-                          void *partials, void *cand_out, int exact, void *stream);
+                          void *partials, void *cand_out, int exact, int n_steps, void *stream);
 /* seed: arg-max of the CURRENT dist array -> cand_out (all +inf gives frame 0, which is the
  * reference's first centre, kcenters.py:199,282,326-328); resets *state with
  * n_centers = first_center_id (> 0 when continuing from init_centers, kcenters.py:200-206). */
@@ -147,7 +149,7 @@ int eb_kcenters_step_feat(const void *X, int64_t n, int64_t n_features, int dtyp
                           int64_t frame_offset, const void *cand_in, int n_cand, double *dist,
                           int32_t *assign, int32_t n_clusters_limit, double dist_cutoff,
                           eb_kc_state *state, int64_t *center_list, void *partials,
-                          void *cand_out, void *stream);
+                          void *cand_out, int n_steps, void *stream);
 int eb_kcenters_seed_feat(const void *X, int64_t n, int64_t n_features, int dtype,
                           int64_t frame_offset, const double *dist, int32_t first_center_id,
                           eb_kc_state *state, void *partials, void *cand_out, void *stream);
