@@ -130,9 +130,63 @@ def assign_device(metric, data, centers, frame_idx=None, out_dist=None, out_assi
     return out_dist, out_assign
 
 
+#: the tensor-core screen pays off once there are enough centres to amortise the operand split
+TC_MIN_CENTERS = 64
+#: frames per screen pass (bounds the split-operand scratch: 2 x 12*A_pad bytes per frame)
+TC_CHUNK_FRAMES = 262144
+#: error model of the 3xTF32 screen: |N * d(msd)| <= TC_KAPPA_PER_ATOM * A_pad * sqrt(Ga*Gb).
+#: Measured on B200 (scripts/dev_tc_debug.py): the worst pair is 1.0 * 2^-24 per atom (FP32
+#: accumulation in the tensor core truncates); 8x margin.
+TC_KAPPA_PER_ATOM = 8.0 * 2.0 ** -24
+
+
+def tc_applicable(metric, data, k):
+    return (metric.is_rmsd and k >= TC_MIN_CENTERS and data.a_pad % 16 == 0
+            and len(data) >= 128)
+
+
+def assign_device_tc(metric, data, centers, k=None, stats=None):
+    """Dense nearest-centre pass through the tcgen05 screen + exact re-score
+    (csrc/eb_tc_screen.cu).  Same result as ``assign_device`` (the exact path decides)."""
+    n = len(data)
+    k = len(centers) if k is None else int(k)
+    dev = data.xyz.device
+    lib = _lib.load()
+    out_dist = torch.full((n,), float("inf"), dtype=torch.float32, device=dev)
+    out_assign = torch.zeros((n,), dtype=torch.int32, device=dev)
+    cand = torch.zeros((n,), dtype=torch.int32, device=dev)
+    chunk = min(n, TC_CHUNK_FRAMES)
+    scratch = torch.empty(int(lib.eb_tc_scratch_bytes(chunk, data.n_atoms, k)),
+                          dtype=torch.uint8, device=dev)
+    kappa = TC_KAPPA_PER_ATOM * data.a_pad
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        _lib.call("eb_rmsd_assign_tc", ptr(data.xyz[lo:]), ptr(data.traces[lo:]), hi - lo,
+                  data.n_atoms, ptr(centers.xyz), ptr(centers.traces), k, float(kappa),
+                  ptr(out_dist[lo:]), ptr(out_assign[lo:]), ptr(cand[lo:]), ptr(scratch), None,
+                  1, stream_ptr())
+    overflow = torch.nonzero(cand < 0).view(-1)
+    if stats is not None:
+        stats["survivors_mean"] = float(cand.clamp(min=0).float().mean().cpu())
+        stats["overflow_frames"] = int(overflow.numel())
+    if overflow.numel() > 0:
+        # more than 128 centres survived the screen for these frames: exact pass over all centres
+        assign_device(metric, data, centers, frame_idx=overflow.to(torch.int64).contiguous(),
+                      out_dist=out_dist, out_assign=out_assign, accumulate=False, scatter=True,
+                      k=k)
+    return out_dist, out_assign
+
+
+def assign_device_auto(metric, data, centers, k=None):
+    kk = len(centers) if k is None else int(k)
+    if tc_applicable(metric, data, kk):
+        return assign_device_tc(metric, data, centers, k=kk)
+    return assign_device(metric, data, centers, k=kk)
+
+
 def assign_host(metric, trajectory, cluster_centers):
     """assign_to_nearest_center (cluster/util.py:159-205) -> (int64[n], float64[n]) numpy."""
     data = metric.to_device(trajectory)
     centers = centers_to_device(metric, cluster_centers, data)
-    d, a = assign_device(metric, data, centers)
+    d, a = assign_device_auto(metric, data, centers)
     return a.cpu().numpy().astype(np.int64), d.cpu().numpy().astype(np.float64)

@@ -157,6 +157,22 @@ int eb_kcenters_seed_feat(const void *X, int64_t n, int64_t n_features, int dtyp
 int eb_feat_one_to_all(const void *X, int64_t n, int64_t n_features, int dtype, int metric,
                        const void *y, double *out, void *stream);
 
+/* ---- K3 on the tensor cores: 3xTF32 tcgen05 screen + exact re-score ----------------------
+ * Same result as eb_rmsd_assign (dense pass over all n frames, no accumulate): a tcgen05 GEMM
+ * with a fused QCP epilogue bounds every (frame, centre) distance; only centres whose lower
+ * bound does not exceed the frame's best upper bound survive (error model: |d msd| <=
+ * kappa * sqrt(Ga*Gb) / n_atoms) and are re-scored exactly in float64 with the reference's
+ * strict-'<' centre order.  cand_count[f] receives the number of survivors of frame f, or -1 if
+ * more than 128 survived; those frames are NOT written and must be sent through eb_rmsd_assign
+ * (frame_idx subset).  scratch: eb_tc_scratch_bytes(n, n_atoms, k).  Requires
+ * eb_rmsd_apad(n_atoms) % 16 == 0.  mode 0 is a debugging aid: dbg (n*k*9 floats) receives the
+ * approximate inner-product matrices and nothing else is written. */
+size_t eb_tc_scratch_bytes(int64_t n, int n_atoms, int32_t k);
+int eb_rmsd_assign_tc(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
+                      const float *centers_soa, const double *center_traces, int32_t k,
+                      double kappa, float *out_dist, int32_t *out_assign, int32_t *cand_count,
+                      void *scratch, float *dbg, int mode, void *stream);
+
 /* ---- K3 for feature vectors (same contract as eb_rmsd_assign) */
 int eb_feat_assign(const void *X, int64_t n, int64_t n_features, int dtype, int metric,
                    const void *centers, int32_t k, const int64_t *frame_idx, int64_t n_idx,
