@@ -170,7 +170,7 @@ def assign_device_tc(metric, data, centers, k=None, stats=None):
         stats["survivors_mean"] = float(cand.clamp(min=0).float().mean().cpu())
         stats["overflow_frames"] = int(overflow.numel())
     if overflow.numel() > 0:
-        # more than 128 centres survived the screen for these frames: exact pass over all centres
+        # a candidate list overflowed for these frames: exact pass over all centres
         assign_device(metric, data, centers, frame_idx=overflow.to(torch.int64).contiguous(),
                       out_dist=out_dist, out_assign=out_assign, accumulate=False, scatter=True,
                       k=k)

@@ -13,8 +13,9 @@
 // D_0, D_1, D_2), so the 3x3 matrix is never exchanged between threads or written to memory.
 // TF32 has 10 mantissa bits, so every operand is split x = hi + lo (hi = x truncated to TF32,
 // lo = x - hi, exact) and D = Ahi.Bhi + Ahi.Blo + Alo.Bhi is accumulated in FP32 in TMEM
-// (3xTF32).  Operands are pre-split in global memory by k_split_tf32 and arrive by TMA
-// (64-byte rows, SWIZZLE_64B) in a 3-stage mbarrier ring; one elected thread issues
+// (3xTF32).  Operands are pre-split AND pre-packed by k_pack_tf32 into the exact swizzled
+// shared-memory image of every tile (64-byte rows, SWIZZLE_64B), so one pipeline stage arrives
+// with two contiguous bulk copies (cp.async.bulk) in a 3-stage mbarrier ring; one elected thread issues
 // tcgen05.mma.kind::tf32 (M=128 frames, N=96 = 32 centres x 3), 9 MMAs per 8 atoms.
 //
 // Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2-5
@@ -34,38 +35,53 @@ constexpr int A_TILE = BM * BK * 4;      // 8192
 constexpr int B_TILE = BN * BK * 4;      // 6144
 constexpr int STAGE_BYTES = 6 * A_TILE + 2 * B_TILE;  // {hi,lo} x 3 coords of A, {hi,lo} of B
 constexpr int TMEM_COLS = 512;           // 3 accumulators x 96 columns = 288 -> power of two
-constexpr int THREADS = 192;
-constexpr int MAX_CAND = 128;            // survivors kept per frame before falling back
+constexpr int THREADS = 64 + 128 * 2;  // producer, MMA, 8 epilogue warps
+constexpr int MAX_CAND = 32;   // survivors kept per candidate list
+constexpr int MAX_SEG = 4;     // centre segments: CTAs sharing a frame tile hit it in L2
+constexpr int EPI_HALVES = 2;  // two epilogue warps per TMEM lane quarter, 16 centres each
+constexpr int MAX_LISTS = MAX_SEG * EPI_HALVES;  // candidate lists per frame
 
-// ---- operand split -------------------------------------------------------------------------
+// ---- operand split + packing -----------------------------------------------------------------
+// Writes, for every (tile T, k-block kb, sub-row-set s, hi|lo), the exact shared-memory image of
+// the MMA operand tile (RT rows x 64 bytes, SWIZZLE_64B: 16-byte chunk c of row r lives at chunk
+// c ^ ((r >> 1) & 3)), contiguously in global memory, so that a whole pipeline stage arrives
+// with ONE bulk copy instead of hundreds of 64-byte TMA row requests.
+//   image index = (((T * KB + kb) * S + s) * 2 + hl) * (RT * 64 bytes)
+//   source row  = (T * RT + r) * S + s   of the (rows_total x A_pad) float matrix `x`
+// Frames: RT = 128, S = 3 (the three coordinate rows of a frame); centres: RT = 96, S = 1.
 __global__ void __launch_bounds__(256)
-k_split_tf32(const float4 *__restrict__ x, long n4, float4 *__restrict__ hi,
-             float4 *__restrict__ lo)
+k_pack_tf32(const float *__restrict__ x, long rows_total, int A_pad, int RT, int S, long n_tiles,
+            unsigned char *__restrict__ img)
 {
-    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < n4;
+    const int Q = A_pad >> 2;  // float4 per row
+    const int KB = A_pad / BK;
+    const long total = n_tiles * RT * S * (long)Q;
+    const size_t tile_bytes = (size_t)RT * 64;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (long)gridDim.x * blockDim.x) {
-        const float4 v = x[t];
+        const int q = (int)(t % Q);
+        const long rr = t / Q;           // (T, r, s) flattened as ((T*RT + r)*S + s)
+        const int sidx = (int)(rr % S);
+        const long tr = rr / S;          // T*RT + r
+        const long T = tr / RT;
+        const int r = (int)(tr - T * RT);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rr < rows_total) v = __ldg(reinterpret_cast<const float4 *>(x + (size_t)rr * A_pad) + q);
         float4 h, l;
         h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
         h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
         h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
         h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
         l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-        hi[t] = h;
-        lo[t] = l;
+        const int kb = q >> 2, c = q & 3;
+        const size_t base = ((((size_t)T * KB + kb) * S + sidx) * 2) * tile_bytes +
+                            (size_t)r * 64 + (size_t)((c ^ ((r >> 1) & 3)) << 4);
+        *reinterpret_cast<float4 *>(img + base) = h;
+        *reinterpret_cast<float4 *>(img + base + tile_bytes) = l;
     }
 }
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
-__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tmap, int c0, int c1,
-                                            int c2, uint64_t *bar)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
-        "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
-        "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar)
@@ -112,6 +128,56 @@ constexpr uint32_t kIdesc = (1u << 4)          // D format F32
                             | (2u << 10)       // B format TF32
                             | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
+
+// FP32 QCP for the screen, four independent pairs at a time (instruction-level parallelism: an
+// epilogue warp has its scheduler almost to itself).  Inputs are normalised by s = sqrt(Ga*Gb)
+// so that |M'| <= 1 and the start g = (Ga+Gb)/(2s) >= 1 whatever the size of the molecule;
+// lam' = lambda_max / s.  Eight Newton steps from above, no early exit; `dl` returns the size
+// of the last step so that the caller can refuse to trust a solve that has not settled.
+__device__ __forceinline__ void qcp4_f32(const float M[4][9], const float g[4], float lam[4],
+                                         float dl[4])
+{
+    float c2[4], c1[4], c0[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const float Sxx = M[p][0], Sxy = M[p][1], Sxz = M[p][2];
+        const float Syx = M[p][3], Syy = M[p][4], Syz = M[p][5];
+        const float Szx = M[p][6], Szy = M[p][7], Szz = M[p][8];
+        const float k00 = Sxx + Syy + Szz, k01 = Syz - Szy, k02 = Szx - Sxz, k03 = Sxy - Syx;
+        const float k11 = Sxx - Syy - Szz, k12 = Sxy + Syx, k13 = Szx + Sxz;
+        const float k22 = -Sxx + Syy - Szz, k23 = Syz + Szy;
+        const float k33 = -Sxx - Syy + Szz;
+        c2[p] = -2.0f * (Sxx * Sxx + Sxy * Sxy + Sxz * Sxz + Syx * Syx + Syy * Syy + Syz * Syz +
+                         Szx * Szx + Szy * Szy + Szz * Szz);
+        c1[p] = -8.0f * (Sxx * (Syy * Szz - Syz * Szy) - Sxy * (Syx * Szz - Syz * Szx) +
+                         Sxz * (Syx * Szy - Syy * Szx));
+        const float a01 = k00 * k11 - k01 * k01, a02 = k00 * k12 - k02 * k01;
+        const float a03 = k00 * k13 - k03 * k01, a12 = k01 * k12 - k02 * k11;
+        const float a13 = k01 * k13 - k03 * k11, a23 = k02 * k13 - k03 * k12;
+        const float b01 = k02 * k13 - k12 * k03, b02 = k02 * k23 - k22 * k03;
+        const float b03 = k02 * k33 - k23 * k03, b12 = k12 * k23 - k22 * k13;
+        const float b13 = k12 * k33 - k23 * k13, b23 = k22 * k33 - k23 * k23;
+        c0[p] = a01 * b23 - a02 * b13 + a03 * b12 + a12 * b03 - a13 * b02 + a23 * b01;
+        lam[p] = g[p];
+        dl[p] = 0.f;
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const float l = lam[p], l2 = l * l;
+            const float b = (l2 + c2[p]) * l;
+            const float a = b + c1[p];
+            const float den = 2.0f * l2 * l + b + a;
+            const float delta = (den != 0.0f) ? __fdividef(a * l + c0[p], den) : 0.0f;
+            lam[p] = l - delta;
+            dl[p] = delta;
+        }
+    }
+}
+// slack for the FP32 solve, relative to (Ga+Gb)/2, in units of N*msd (measured: < 8e-6)
+constexpr double kQcpSlack = 6.4e-5;
+
 struct Smem {
     uint64_t full[STAGES];
     uint64_t empty[STAGES];
@@ -124,11 +190,10 @@ struct Smem {
 // mode 1: screen, maintain per-frame candidate lists
 template <int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
-k_tc_screen(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
-            const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+k_tc_screen(const unsigned char *__restrict__ a_img, const unsigned char *__restrict__ b_img,
             const double *__restrict__ traces, const double *__restrict__ ctraces, long n, int k,
             int n_atoms, int A_pad, double kappa, float *dbg, int *cand_count, int *cand_list,
-            float *cand_bound)
+            float *cand_bound, float *cand_umin, int n_seg)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *tiles = smem_raw;
@@ -138,6 +203,10 @@ k_tc_screen(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     const int KB = A_pad / BK;
     const int n_ct = (k + NC - 1) / NC;
     const long n_ft = (n + BM - 1) / BM;
+    // work item = (frame tile, centre segment); consecutive CTAs take the segments of the SAME
+    // frame tile, so its A operand is fetched from DRAM once and then served by L2
+    const long n_items = n_ft * n_seg;
+    const int ct_per_seg = (n_ct + n_seg - 1) / n_seg;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -145,7 +214,7 @@ k_tc_screen(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             mbar_init(&sm->empty[s], 1);
         }
         mbar_init(&sm->tmem_full, 1);
-        mbar_init(&sm->tmem_empty, 4);
+        mbar_init(&sm->tmem_empty, 4 * EPI_HALVES);
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -162,28 +231,22 @@ k_tc_screen(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     if (warp == 0) {
         // ===================== TMA producer ===================================================
         if (lane == 0) {
-            tma_prefetch_desc(&tm_a_hi);
-            tma_prefetch_desc(&tm_a_lo);
-            tma_prefetch_desc(&tm_b_hi);
-            tma_prefetch_desc(&tm_b_lo);
             int stage = 0;
             uint32_t phase = 0;
-            for (long ft = blockIdx.x; ft < n_ft; ft += gridDim.x) {
-                for (int ct = 0; ct < n_ct; ++ct) {
+            for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const long ft = item / n_seg;
+                const int seg = (int)(item - ft * n_seg);
+                const int ct_hi = min(n_ct, (seg + 1) * ct_per_seg);
+                for (int ct = seg * ct_per_seg; ct < ct_hi; ++ct) {
                     for (int kb = 0; kb < KB; ++kb) {
                         mbar_wait(&sm->empty[stage], phase ^ 1);
                         unsigned char *st = tiles + (size_t)stage * STAGE_BYTES;
                         mbar_expect_tx(&sm->full[stage], STAGE_BYTES);
-                        for (int i = 0; i < 3; ++i) {
-                            tma_load_3d(st + (2 * i) * A_TILE, &tm_a_hi, kb * BK, i,
-                                        (int)(ft * BM), &sm->full[stage]);
-                            tma_load_3d(st + (2 * i + 1) * A_TILE, &tm_a_lo, kb * BK, i,
-                                        (int)(ft * BM), &sm->full[stage]);
-                        }
-                        tma_load_2d(st + 6 * A_TILE, &tm_b_hi, kb * BK, ct * BN,
-                                    &sm->full[stage]);
-                        tma_load_2d(st + 6 * A_TILE + B_TILE, &tm_b_lo, kb * BK, ct * BN,
-                                    &sm->full[stage]);
+                        // stage image = [coord i][hi|lo] A tiles (48 KB) then [hi|lo] B tiles
+                        bulk_g2s(st, a_img + ((size_t)ft * KB + kb) * (6 * A_TILE), 6 * A_TILE,
+                                 &sm->full[stage]);
+                        bulk_g2s(st + 6 * A_TILE, b_img + ((size_t)ct * KB + kb) * (2 * B_TILE),
+                                 2 * B_TILE, &sm->full[stage]);
                         if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1;
@@ -197,8 +260,12 @@ k_tc_screen(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0, tphase = 0;
-            for (long ft = blockIdx.x; ft < n_ft; ft += gridDim.x) {
-                for (int ct = 0; ct < n_ct; ++ct) {
+            for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const long ft = item / n_seg;
+                const int seg = (int)(item - ft * n_seg);
+                const int ct_hi = min(n_ct, (seg + 1) * ct_per_seg);
+                (void)ft;
+                for (int ct = seg * ct_per_seg; ct < ct_hi; ++ct) {
                     mbar_wait(&sm->tmem_empty, tphase ^ 1);  // epilogue drained the accumulators
                     tc_fence_after();
                     for (int kb = 0; kb < KB; ++kb) {
@@ -234,23 +301,34 @@ k_tc_screen(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         }
     } else {
         // ===================== epilogue: TMEM -> registers -> QCP ============================
-        const int q = warp & 3;                    // TMEM lane quarter of this warp
+        // warp w (2..9): TMEM lane quarter w & 3 (hardware rule), centre half (w - 2) >> 2
+        const int q = warp & 3;
+        const int hh = (warp - 2) >> 2;            // which 16 of the tile's 32 centres
         const int row = q * 32 + lane;             // frame within the tile
+        const int n_lists = n_seg * EPI_HALVES;
         uint32_t tphase = 0;
-        for (long ft = blockIdx.x; ft < n_ft; ft += gridDim.x) {
+        for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const long ft = item / n_seg;
+            const int seg = (int)(item - ft * n_seg);
+            const int ct_hi = min(n_ct, (seg + 1) * ct_per_seg);
             const long f = ft * BM + row;
             const bool fvalid = f < n;
             const double Ga = fvalid ? traces[f] : 0.0;
-            // screen state of this frame (thread-private across all centre tiles)
+            const float sa = sqrtf((float)Ga);
+            // screen state of this (frame, list): thread-private across the centre tiles; all
+            // bounds are kept in units of N * msd
             double umin = 1e300;
             int ncand = 0;
-            for (int ct = 0; ct < n_ct; ++ct) {
+            const int lid = seg * EPI_HALVES + hh;
+            const size_t slot = ((size_t)(fvalid ? f : 0) * n_lists + lid) * MAX_CAND;
+            for (int ct = seg * ct_per_seg; ct < ct_hi; ++ct) {
                 mbar_wait(&sm->tmem_full, tphase);
                 tphase ^= 1;
                 tc_fence_after();
                 const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-                for (int g = 0; g < NC / 8; ++g) {  // 8 centres = 24 columns per accumulator
+                for (int gg = 0; gg < 2; ++gg) {   // 8 centres = 24 columns per accumulator
+                    const int g = hh * 2 + gg;
                     float m[3][24];
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
@@ -260,30 +338,57 @@ k_tc_screen(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                         tc_ld8(lane_addr + col + 16, &m[i][16]);
                     }
                     tc_wait_ld();
+                    if (MODE == 0) {
 #pragma unroll
-                    for (int cc = 0; cc < 8; ++cc) {
-                        const int c = ct * NC + g * 8 + cc;
-                        if (!fvalid || c >= k) continue;
-                        if (MODE == 0) {
+                        for (int cc = 0; cc < 8; ++cc) {
+                            const int c = ct * NC + g * 8 + cc;
+                            if (!fvalid || c >= k) continue;
                             float *o = dbg + ((size_t)f * k + c) * 9;
 #pragma unroll
                             for (int i = 0; i < 3; ++i)
 #pragma unroll
                                 for (int j = 0; j < 3; ++j) o[3 * i + j] = m[i][3 * cc + j];
-                        } else {
-                            double M[9];
+                        }
+                    }
+#pragma unroll
+                    for (int bq = 0; bq < (MODE == 0 ? 0 : 2); ++bq) {   // two batches of four
+                        float Mn[4][9], gq[4], scf[4], lam[4], dl[4];
+                        double Gb[4];
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) {
+                            const int cc = bq * 4 + p;
+                            const int c = min(ct * NC + g * 8 + cc, k - 1);
+                            Gb[p] = __ldg(ctraces + c);
+                            scf[p] = fmaxf(sa * sqrtf((float)Gb[p]), 1e-30f);
+                            const float inv = __frcp_rn(scf[p]);
+                            gq[p] = (float)(0.5 * (Ga + Gb[p])) * inv;
 #pragma unroll
                             for (int i = 0; i < 3; ++i)
 #pragma unroll
-                                for (int j = 0; j < 3; ++j) M[3 * i + j] = (double)m[i][3 * cc + j];
-                            const double Gb = ctraces[c];
-                            const double msd = qcp_msd(M, Ga, Gb, n_atoms);
-                            const double e = kappa * sqrt(Ga * Gb) / (double)n_atoms;
-                            const double lo = msd - e, up = msd + e;
+                                for (int j = 0; j < 3; ++j) Mn[p][3 * i + j] = m[i][3 * cc + j] * inv;
+                        }
+                        qcp4_f32(Mn, gq, lam, dl);
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) {
+                            const int c = ct * NC + g * 8 + bq * 4 + p;
+                            if (!fvalid || c >= k) continue;
+                            const double half = 0.5 * (Ga + Gb[p]);
+                            const double sc = (double)scf[p];
+                            const double v = 2.0 * (half - sc * (double)lam[p]);  // N * msd
+                            const double e = kappa * sc + kQcpSlack * half;
+                            // Newton from above decreases monotonically towards lambda_max, so
+                            // an unsettled solve still OVER-estimates lambda: v - e stays a valid
+                            // lower bound, only the upper bound needs a settled solve.  A solve
+                            // that left the feasible range proves nothing: keep the pair.
+                            const bool finite = (lam[p] == lam[p]) && lam[p] <= gq[p] * 1.001f &&
+                                                lam[p] >= -gq[p];
+                            const bool settled = fabsf(dl[p]) <= 4e-6f * fabsf(gq[p]);
+                            const double lo = finite ? v - e : -1e300;
+                            const double up = (finite && settled) ? v + e : 1e300;
                             if (lo <= umin) {
                                 if (ncand < MAX_CAND) {
-                                    cand_list[(size_t)f * MAX_CAND + ncand] = c;
-                                    cand_bound[(size_t)f * MAX_CAND + ncand] = __double2float_rd(lo);
+                                    cand_list[slot + ncand] = c;
+                                    cand_bound[slot + ncand] = __double2float_rd(lo);
                                 }
                                 ++ncand;
                             }
@@ -291,18 +396,18 @@ k_tc_screen(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                             if (ncand == MAX_CAND + 1) {
                                 // list overflowed: compact it against the current bound once
                                 int w = 0;
-                                for (int s = 0; s < MAX_CAND; ++s) {
-                                    const float b = cand_bound[(size_t)f * MAX_CAND + s];
-                                    const int cs = cand_list[(size_t)f * MAX_CAND + s];
+                                for (int s2 = 0; s2 < MAX_CAND; ++s2) {
+                                    const float b = cand_bound[slot + s2];
+                                    const int cs = cand_list[slot + s2];
                                     if ((double)b <= umin) {
-                                        cand_list[(size_t)f * MAX_CAND + w] = cs;
-                                        cand_bound[(size_t)f * MAX_CAND + w] = b;
+                                        cand_list[slot + w] = cs;
+                                        cand_bound[slot + w] = b;
                                         ++w;
                                     }
                                 }
                                 if (w < MAX_CAND) {
-                                    cand_list[(size_t)f * MAX_CAND + w] = c;
-                                    cand_bound[(size_t)f * MAX_CAND + w] = __double2float_rd(lo);
+                                    cand_list[slot + w] = c;
+                                    cand_bound[slot + w] = __double2float_rd(lo);
                                     ncand = w + 1;
                                 } else {
                                     ncand = MAX_CAND + 2;  // sticky overflow: exact fallback
@@ -316,20 +421,21 @@ k_tc_screen(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 if (lane == 0) mbar_arrive(&sm->tmem_empty);
             }
             if (MODE == 1 && fvalid) {
+                cand_umin[(size_t)f * n_lists + lid] = __double2float_ru(fmin(umin, 3.0e38));
                 if (ncand > MAX_CAND) {
-                    cand_count[f] = -1;  // overflow -> the host routes this frame to the exact path
+                    cand_count[(size_t)f * n_lists + lid] = -1;  // overflow -> exact path (host)
                 } else {
-                    // final prune against the final bound (order preserved: ascending centre id)
-                    int w = 0;
-                    for (int s = 0; s < ncand; ++s) {
-                        const float b = cand_bound[(size_t)f * MAX_CAND + s];
-                        const int cs = cand_list[(size_t)f * MAX_CAND + s];
+                    int w = 0;  // final prune against the final bound of this list
+                    for (int s2 = 0; s2 < ncand; ++s2) {
+                        const float b = cand_bound[slot + s2];
+                        const int cs = cand_list[slot + s2];
                         if ((double)b <= umin) {
-                            cand_list[(size_t)f * MAX_CAND + w] = cs;
+                            cand_list[slot + w] = cs;
+                            cand_bound[slot + w] = b;
                             ++w;
                         }
                     }
-                    cand_count[f] = w;
+                    cand_count[(size_t)f * n_lists + lid] = w;
                 }
             }
         }
@@ -349,8 +455,9 @@ k_tc_screen(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 __global__ void __launch_bounds__(256)
 k_rescore(const float *__restrict__ xyz, const double *__restrict__ traces, long n, int n_atoms,
           int A_pad, const float *__restrict__ centers, const double *__restrict__ ctraces,
-          const int *__restrict__ cand_count, const int *__restrict__ cand_list, float *out_dist,
-          int *out_assign)
+          const int *__restrict__ cand_count, const int *__restrict__ cand_list,
+          const float *__restrict__ cand_bound, const float *__restrict__ cand_umin, int n_seg,
+          float *out_dist, int *out_assign, int *frame_flag)
 {
     const int lane = threadIdx.x & 31, g = lane >> 3, l8 = lane & 7;
     const int A4 = A_pad >> 2;
@@ -360,60 +467,68 @@ k_rescore(const float *__restrict__ xyz, const double *__restrict__ traces, long
          fb += groups) {
         const long f = fb + g;
         const bool valid = f < n;
-        const int cnt = valid ? cand_count[f] : 0;
-        int cnt_max = cnt;
-        cnt_max = max(cnt_max, __shfl_xor_sync(0xffffffffu, cnt_max, 8));
-        cnt_max = max(cnt_max, __shfl_xor_sync(0xffffffffu, cnt_max, 16));
+        // merge the segments: global upper bound, overflow if any segment overflowed
+        float U = INFINITY;
+        bool overflow = false;
+        int total = 0;
+        if (valid) {
+            for (int sgm = 0; sgm < n_seg; ++sgm) {
+                U = fminf(U, cand_umin[(size_t)f * n_seg + sgm]);
+                const int cnt = cand_count[(size_t)f * n_seg + sgm];
+                overflow |= cnt < 0;
+                total += max(cnt, 0);
+            }
+        }
         float best_d = INFINITY;
-        int best_c = 0;
+        int best_c = 0, evaluated = 0;
         const float4 *px = reinterpret_cast<const float4 *>(xyz + (size_t)(valid ? f : 0) * stride);
-        for (int s = 0; s < cnt_max; ++s) {
-            const bool act = valid && s < cnt;
-            const int c = act ? cand_list[(size_t)f * MAX_CAND + s] : 0;
-            const float4 *pc = reinterpret_cast<const float4 *>(centers + (size_t)c * stride);
-            double m[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-            if (act) {
-                for (int j = l8; j < A4; j += 8) {
-                    const float4 x = __ldg(px + j), y = __ldg(px + A4 + j), z = __ldg(px + 2 * A4 + j);
-                    const float4 cx = __ldg(pc + j), cy = __ldg(pc + A4 + j), cz = __ldg(pc + 2 * A4 + j);
-                    acc_atom(m, x.x, y.x, z.x, (double)cx.x, (double)cy.x, (double)cz.x);
-                    acc_atom(m, x.y, y.y, z.y, (double)cx.y, (double)cy.y, (double)cz.y);
-                    acc_atom(m, x.z, y.z, z.z, (double)cx.z, (double)cy.z, (double)cz.z);
-                    acc_atom(m, x.w, y.w, z.w, (double)cx.w, (double)cy.w, (double)cz.w);
+        for (int sgm = 0; sgm < n_seg; ++sgm) {
+            const int cnt = (valid && !overflow) ? cand_count[(size_t)f * n_seg + sgm] : 0;
+            int cnt_max = cnt;
+            cnt_max = max(cnt_max, __shfl_xor_sync(0xffffffffu, cnt_max, 8));
+            cnt_max = max(cnt_max, __shfl_xor_sync(0xffffffffu, cnt_max, 16));
+            const size_t slot = ((size_t)(valid ? f : 0) * n_seg + sgm) * MAX_CAND;
+            for (int s = 0; s < cnt_max; ++s) {
+                const bool act = s < cnt && cand_bound[slot + s] <= U;
+                const int c = act ? cand_list[slot + s] : 0;
+                const float4 *pc = reinterpret_cast<const float4 *>(centers + (size_t)c * stride);
+                double m[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                if (act) {
+                    for (int j = l8; j < A4; j += 8) {
+                        const float4 x = __ldg(px + j), y = __ldg(px + A4 + j),
+                                     z = __ldg(px + 2 * A4 + j);
+                        const float4 cx = __ldg(pc + j), cy = __ldg(pc + A4 + j),
+                                     cz = __ldg(pc + 2 * A4 + j);
+                        acc_atom(m, x.x, y.x, z.x, (double)cx.x, (double)cy.x, (double)cz.x);
+                        acc_atom(m, x.y, y.y, z.y, (double)cx.y, (double)cy.y, (double)cz.y);
+                        acc_atom(m, x.z, y.z, z.z, (double)cx.z, (double)cy.z, (double)cz.z);
+                        acc_atom(m, x.w, y.w, z.w, (double)cx.w, (double)cy.w, (double)cz.w);
+                    }
                 }
-            }
-            group8_reduce(m);
-            if (act) {
-                const float d = rmsd_from_msd(qcp_msd(m, traces[f], ctraces[c], n_atoms));
-                if (d < best_d) {
-                    best_d = d;
-                    best_c = c;
+                group8_reduce(m);
+                if (act) {
+                    const float d = rmsd_from_msd(qcp_msd(m, traces[f], ctraces[c], n_atoms));
+                    ++evaluated;
+                    // lists are not globally ordered by centre: lowest centre index on exact
+                    // ties, which is what strict '<' in centre order gives (util.py:201)
+                    if (d < best_d || (d == best_d && c < best_c)) {
+                        best_d = d;
+                        best_c = c;
+                    }
                 }
             }
         }
-        if (valid && l8 == 0 && cnt > 0) {
-            out_dist[f] = best_d;
-            out_assign[f] = best_c;
+        if (valid && l8 == 0) {
+            if (overflow || evaluated == 0) {
+                frame_flag[f] = -1;  // the host sends this frame through the exact kernel
+            } else {
+                frame_flag[f] = evaluated;
+                out_dist[f] = best_d;
+                out_assign[f] = best_c;
+            }
         }
+        (void)total;
     }
-}
-
-static int make_tmap_3d(CUtensorMap *out, const void *base, uint64_t d0, uint64_t d1, uint64_t d2,
-                        uint64_t s1_bytes, uint64_t s2_bytes, uint32_t b0, uint32_t b1,
-                        uint32_t b2, CUtensorMapSwizzle swz)
-{
-    PFN_tmapEncodeTiled enc = tmap_encode_fn();
-    if (!enc) return fail(EB_ERR_CUDA, "%s", "cuTensorMapEncodeTiled entry point unavailable");
-    cuuint64_t gdim[3] = {d0, d1, d2};
-    cuuint64_t gstride[2] = {s1_bytes, s2_bytes};
-    cuuint32_t box[3] = {b0, b1, b2};
-    cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(base), gdim,
-                           gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS)
-        return fail(EB_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed (%s %ld)", "code", (long)r);
-    return EB_OK;
 }
 
 }  // namespace tc
@@ -427,8 +542,10 @@ size_t eb_tc_scratch_bytes(int64_t n, int n_atoms, int32_t k)
 {
     const size_t row = sizeof(float) * 3 * (size_t)rmsd_apad(n_atoms);
     // split copies of frames and centres + candidate lists
-    return 2 * row * (size_t)n + 2 * row * (size_t)(k + tc::NC) +
-           (size_t)n * (sizeof(int) + tc::MAX_CAND * (sizeof(int) + sizeof(float))) + 4096;
+    return 2 * row * (size_t)(n + tc::BM) + 2 * row * (size_t)(k + tc::NC) +
+           (size_t)n * tc::MAX_LISTS *
+               (sizeof(int) + sizeof(float) + tc::MAX_CAND * (sizeof(int) + sizeof(float))) +
+           4096;
 }
 
 // mode 0 (debug): dbg receives the approximate inner-product matrices, n x k x 9 floats.
@@ -449,68 +566,64 @@ int eb_rmsd_assign_tc(const float *xyz_soa, const double *traces, int64_t n, int
     const int A_pad = rmsd_apad(n_atoms);
     EB_CHECK_ARG(A_pad % tc::BK == 0, "rmsd_assign_tc: padded atom count must be a multiple of 16");
     const size_t row = 3 * (size_t)A_pad;  // floats per frame
-    float *a_hi = (float *)scratch;
-    float *a_lo = a_hi + row * n;
-    float *b_hi = a_lo + row * n;
-    const size_t kb_rows = (size_t)k + tc::NC;  // slack so TMA boxes never start out of bounds
-    float *b_lo = b_hi + row * kb_rows;
-    int *cand_list = (int *)(b_lo + row * kb_rows);
-    float *cand_bound = (float *)(cand_list + (size_t)n * tc::MAX_CAND);
+    // packed operand images (tile-padded): frames then centres
+    const size_t a_rows = (size_t)((n + tc::BM - 1) / tc::BM) * tc::BM;   // frames, padded
+    const size_t c_rows = (size_t)((k + tc::NC - 1) / tc::NC) * tc::NC;   // centres, padded
+    unsigned char *a_img = (unsigned char *)scratch;
+    unsigned char *b_img = a_img + 2 * sizeof(float) * row * a_rows;
+    unsigned char *lists = b_img + 2 * sizeof(float) * row * c_rows;
+    const int n_ct_total = (k + tc::NC - 1) / tc::NC;
+    const int n_seg = n_ct_total < tc::MAX_SEG ? n_ct_total : tc::MAX_SEG;
+    int *cand_list = (int *)lists;
+    float *cand_bound = (float *)(cand_list + (size_t)n * tc::MAX_LISTS * tc::MAX_CAND);
+    float *cand_umin = cand_bound + (size_t)n * tc::MAX_LISTS * tc::MAX_CAND;
+    int *seg_count = (int *)(cand_umin + (size_t)n * tc::MAX_LISTS);
 
     {
-        const long n4 = (long)(row * n / 4);
-        long blocks = (n4 + 255) / 256;
-        if (blocks > 16L * sm_count()) blocks = 16L * sm_count();
-        tc::k_split_tf32<<<(int)blocks, 256, 0, s>>>((const float4 *)xyz_soa, n4, (float4 *)a_hi,
-                                                     (float4 *)a_lo);
+        const long a_tiles = (n + tc::BM - 1) / tc::BM;
+        long total = a_tiles * tc::BM * 3 * (long)(A_pad / 4);
+        long blocks = (total + 255) / 256;
+        if (blocks > 32L * sm_count()) blocks = 32L * sm_count();
+        tc::k_pack_tf32<<<(int)blocks, 256, 0, s>>>(xyz_soa, 3L * n, A_pad, tc::BM, 3, a_tiles,
+                                                    a_img);
         EB_LAUNCH_CHECK();
-        const long k4 = (long)(row * k / 4);
-        blocks = (k4 + 255) / 256;
-        tc::k_split_tf32<<<(int)blocks, 256, 0, s>>>((const float4 *)centers_soa, k4,
-                                                     (float4 *)b_hi, (float4 *)b_lo);
+        const long b_tiles = (k + tc::NC - 1) / tc::NC;
+        total = b_tiles * tc::BN * (long)(A_pad / 4);
+        blocks = (total + 255) / 256;
+        if (blocks > 32L * sm_count()) blocks = 32L * sm_count();
+        tc::k_pack_tf32<<<(int)blocks, 256, 0, s>>>(centers_soa, 3L * k, A_pad, tc::BN, 1, b_tiles,
+                                                    b_img);
         EB_LAUNCH_CHECK();
     }
-    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
-    const uint64_t pitch = (uint64_t)A_pad * 4;
-    int rc;
-    rc = tc::make_tmap_3d(&ta_hi, a_hi, A_pad, 3, (uint64_t)n, pitch, 3 * pitch, tc::BK, 1, tc::BM,
-                          CU_TENSOR_MAP_SWIZZLE_64B);
-    if (rc) return rc;
-    rc = tc::make_tmap_3d(&ta_lo, a_lo, A_pad, 3, (uint64_t)n, pitch, 3 * pitch, tc::BK, 1, tc::BM,
-                          CU_TENSOR_MAP_SWIZZLE_64B);
-    if (rc) return rc;
-    rc = make_tmap_2d(&tb_hi, b_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 3 * (uint64_t)k,
-                      (uint64_t)A_pad, pitch, tc::BN, tc::BK, CU_TENSOR_MAP_SWIZZLE_64B);
-    if (rc) return rc;
-    rc = make_tmap_2d(&tb_lo, b_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 3 * (uint64_t)k,
-                      (uint64_t)A_pad, pitch, tc::BN, tc::BK, CU_TENSOR_MAP_SWIZZLE_64B);
-    if (rc) return rc;
-
     const size_t smem = (size_t)tc::STAGES * tc::STAGE_BYTES + sizeof(tc::Smem) + 1024;
     const long n_ft = (n + tc::BM - 1) / tc::BM;
-    const int grid = (int)(n_ft < sm_count() ? n_ft : sm_count());
+    const long n_items = n_ft * n_seg;
+    const int grid = (int)(n_items < sm_count() ? n_items : sm_count());
     if (mode == 0) {
         EB_CHECK_ARG(dbg, "rmsd_assign_tc: debug buffer missing");
         EB_CUDA(cudaFuncSetAttribute(tc::k_tc_screen<0>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc::k_tc_screen<0><<<grid, tc::THREADS, smem, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, traces,
+        tc::k_tc_screen<0><<<grid, tc::THREADS, smem, s>>>(a_img, b_img, traces,
                                                            center_traces, n, k, n_atoms, A_pad,
-                                                           kappa, dbg, nullptr, nullptr, nullptr);
+                                                           kappa, dbg, nullptr, nullptr, nullptr,
+                                                           nullptr, n_seg);
         EB_LAUNCH_CHECK();
         return EB_OK;
     }
     EB_CHECK_ARG(out_dist && out_assign && cand_count, "rmsd_assign_tc: null output");
     EB_CUDA(cudaFuncSetAttribute(tc::k_tc_screen<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
-    tc::k_tc_screen<1><<<grid, tc::THREADS, smem, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, traces,
+    tc::k_tc_screen<1><<<grid, tc::THREADS, smem, s>>>(a_img, b_img, traces,
                                                        center_traces, n, k, n_atoms, A_pad, kappa,
-                                                       nullptr, cand_count, cand_list, cand_bound);
+                                                       nullptr, seg_count, cand_list, cand_bound,
+                                                       cand_umin, n_seg);
     EB_LAUNCH_CHECK();
     long blocks = (n + 31) / 32;
     if (blocks > 8L * sm_count()) blocks = 8L * sm_count();
     tc::k_rescore<<<(int)blocks, 256, 0, s>>>(xyz_soa, traces, n, n_atoms, A_pad, centers_soa,
-                                              center_traces, cand_count, cand_list, out_dist,
-                                              out_assign);
+                                              center_traces, seg_count, cand_list, cand_bound,
+                                              cand_umin, n_seg * tc::EPI_HALVES, out_dist,
+                                              out_assign, cand_count);
     EB_LAUNCH_CHECK();
     return EB_OK;
 }

@@ -162,9 +162,9 @@ int eb_feat_one_to_all(const void *X, int64_t n, int64_t n_features, int dtype, 
  * with a fused QCP epilogue bounds every (frame, centre) distance; only centres whose lower
  * bound does not exceed the frame's best upper bound survive (error model: |d msd| <=
  * kappa * sqrt(Ga*Gb) / n_atoms) and are re-scored exactly in float64 with the reference's
- * strict-'<' centre order.  cand_count[f] receives the number of survivors of frame f, or -1 if
- * more than 128 survived; those frames are NOT written and must be sent through eb_rmsd_assign
- * (frame_idx subset).  scratch: eb_tc_scratch_bytes(n, n_atoms, k).  Requires
+ * strict-'<' centre order.  cand_count[f] receives the number of centres re-scored for frame f,
+ * or -1 if a candidate list overflowed (64 per centre segment); those frames are NOT written and
+ * must be sent through eb_rmsd_assign (frame_idx subset).  scratch: eb_tc_scratch_bytes(n, n_atoms, k).  Requires
  * eb_rmsd_apad(n_atoms) % 16 == 0.  mode 0 is a debugging aid: dbg (n*k*9 floats) receives the
  * approximate inner-product matrices and nothing else is written. */
 size_t eb_tc_scratch_bytes(int64_t n, int n_atoms, int32_t k);
