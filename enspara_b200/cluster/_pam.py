@@ -53,7 +53,8 @@ class PamEngine:
         self.counts = torch.zeros(max(self.k, 1), dtype=torch.int64, device=dev)
         self.medoid_global = [int(g) for g in medoid_global_inds]
         self.medoids = self._fetch_frames(self.medoid_global)
-        self.prop = self._fetch_frames([])  # 1-frame scratch, filled per proposal
+        self.prop = self._fetch_frames([])   # 1-frame scratch, filled per proposal
+        self.saved = self._fetch_frames([])  # 1-frame scratch: the medoid a proposal displaces
         self.cost_num = self._sumsq(self.dist)
         self.n_global = self.shard.n_global
 
@@ -111,12 +112,17 @@ class PamEngine:
         self.comm.all_reduce_sum(t)
         return float(t.cpu()[0])
 
-    def _member_counts(self, cid):
-        """Per-rank member counts of cluster cid (np.where(assignments == cid), :611)."""
+    def _refresh_counts(self):
+        """Member counts of every cluster on every rank (len(np.where(assignments == cid)[0]),
+        kmedoids.py:611).  Assignments only change when a proposal is accepted, so the counts
+        are cached on the host between acceptances (one histogram launch + one small D2H)."""
         _lib.call("eb_count_members", ptr(self.assign), self.n, self.k, ptr(self.counts),
                   stream_ptr())
-        local = int(self.counts[cid].cpu())
-        return np.asarray(self.comm.all_gather_object(local), dtype=np.int64)
+        local = self.counts[:self.k].cpu().numpy().astype(np.int64)
+        self.counts_by_rank = np.stack(self.comm.all_gather_object(local))  # (ranks, k)
+
+    def _member_counts(self, cid):
+        return self.counts_by_rank[:, cid]
 
     def _slot_copy(self, dst, j, src, i):
         if self.is_rmsd:
@@ -151,6 +157,8 @@ class PamEngine:
         rs = check_random_state(random_state)
         sh = self.shard
         acceptances = 0
+        if proposals is None:
+            self._refresh_counts()
         for cid in range(self.k):
             # ---- proposal (kmedoids.py:616-628, 482-517) -------------------------------
             if proposals is None:
@@ -191,10 +199,7 @@ class PamEngine:
                 prop_global = max(self.comm.all_gather_object(mine)) if sh.size > 1 else mine
 
             # ---- ambiguous frames against all medoids, proposal in slot cid (:660-670) --
-            if self.is_rmsd:
-                saved = (self.medoids.xyz[cid].clone(), self.medoids.traces[cid].clone())
-            else:
-                saved = (self.medoids.X[cid].clone(),)
+            self._slot_copy(self.saved, 0, self.medoids, cid)
             self._slot_copy(self.medoids, cid, self.prop, 0)
             if n_ambig > 0:
                 _ops.assign_device(self.metric, self.data, self.medoids,
@@ -215,12 +220,10 @@ class PamEngine:
                 self.cost_num = new_num
                 self.medoid_global[cid] = prop_global
                 acceptances += 1
+                if proposals is None and cid + 1 < self.k:
+                    self._refresh_counts()
             else:
-                if self.is_rmsd:
-                    self.medoids.xyz[cid].copy_(saved[0])
-                    self.medoids.traces[cid].copy_(saved[1])
-                else:
-                    self.medoids.X[cid].copy_(saved[0])
+                self._slot_copy(self.medoids, cid, self.saved, 0)
         self.last_cost = self.cost_num / self.n_global
         return acceptances
 
