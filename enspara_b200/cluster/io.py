@@ -1,8 +1,8 @@
 """Loading inputs and writing outputs for the `cluster` app -- the callers either side of the
 hot path.  Behaviour follows the reference's
 /root/reference/enspara/cluster/util.py:315-549 and mpi/io.py:16-194; mdtraj (trajectory
-files) and PyTables (.h5) are imported lazily and only needed for those formats, as in the
-reference.  `.npy` feature files need neither.
+files) is imported lazily and only needed for that format, as in the reference.  `.npy` and
+`.h5` files need neither mdtraj nor PyTables (enspara_b200.util.h5min).
 """
 import logging
 import os
@@ -52,18 +52,28 @@ def load_npy_as_striped(filenames, stride=1):
 
 
 def load_h5_as_striped(filename, stride=1):
-    """Rows of a RaggedArray .h5 striped over ranks (mpi/io.py:16-65); needs PyTables."""
-    try:
-        import tables  # noqa: F401
-    except ImportError:
+    """Node i of an .h5 file is loaded by rank i % size (mpi/io.py:16-65).  Every rank reads
+    the (tiny) node table itself instead of a broadcast from rank 0; PyTables is not needed
+    (enspara_b200.util.h5min)."""
+    from ..util import h5min
+    f = h5min.File(filename)
+    all_keys = sorted(f.keys())
+    all_shapes = [f[k].shape for k in all_keys]
+    global_lengths = [len(range(0, s[0], stride)) for s in all_shapes]
+    if len(all_keys) == 2 and "array" in all_keys and "lengths" in all_keys:
+        raise NotImplementedError(
+            "Parallel loading of RaggedArrays that have been stored as "
+            "arrays and lengths cannot be loaded in parallel.")
+    if len(all_keys) < mpi.size():
         raise ImproperlyConfigured(
-            "Reading '%s' needs PyTables, which is not installed; pass several .npy files "
-            "to --features instead." % filename)
-    arr = ra.load(filename)
-    rows = [np.asarray(arr[i])[::stride] for i in range(len(arr))]
-    global_lengths = [len(r) for r in rows]
-    mine = rows[mpi.rank()::mpi.size()]
-    return global_lengths, np.ascontiguousarray(np.concatenate(mine))
+            "To stripe nodes across workers, at least 1 node per rank must be given. "
+            "World size is %s, number of nodes is %s." % (mpi.size(), len(all_keys)))
+    local = ra.load(filename, keys=all_keys[mpi.rank()::mpi.size()], stride=stride)
+    if hasattr(local, "_data"):
+        local = local._data
+    elif stride != 1:
+        local = local[::stride]      # ra.load returns a single node whole (ra.py:155-158)
+    return global_lengths, np.ascontiguousarray(local)
 
 
 def load_features(features, stride):

@@ -87,72 +87,80 @@ def partition_indices(indices, traj_lengths):
 
 
 # ---------------------------------------------------------------------------------------------
-# save / load.  The reference writes one zlib CArray ``arr_<i>`` per trajectory with PyTables
-# (ra.py:45-89) and needs PyTables to read them back.  PyTables is optional here: `.h5` paths
-# use it when importable, `.npy` / `.npz` paths work everywhere.
+# save / load.  The reference writes one zlib CArray per trajectory with PyTables, named
+# ``arr_<i>`` (ra.py:45-89: tag 'arr', index zero-filled to len(str(n_rows)) + 1 digits; a
+# plain ndarray becomes the single node ``arr_0``) and reads them back with ``ra.load``
+# (ra.py:114-220).  PyTables is not needed here: `.h5` files go through the dependency-free
+# reader/writer in ``enspara_b200.util.h5min`` (reads PyTables' chunked zlib+shuffle nodes,
+# writes contiguous datasets under the same names); `.npy` / `.npz` paths are also accepted.
 # ---------------------------------------------------------------------------------------------
 def _rows(obj):
     if isinstance(obj, RaggedArray):
         return [obj[i] for i in range(len(obj))], False
-    arr = np.asarray(obj)
-    if arr.ndim >= 2:
-        return [arr[i] for i in range(arr.shape[0])], True
-    return [arr], True
+    return [np.asarray(obj)], True
 
 
-def save(path, obj):
-    """Write a (ragged) array.  `.h5`: PyTables layout of the reference; `.npy`: dense array
-    (rows of equal length only); `.npz`: flat data + lengths."""
+def save(path, obj, compression_level=1, tag="arr"):
+    """Write a RaggedArray or ndarray.  `.h5`: the reference's node naming (ra.py:45-89);
+    `.npy`: dense array; `.npz`: flat data + lengths."""
     import os
+    from .util import h5min
     ext = os.path.splitext(path)[1].lower()
-    rows, square = _rows(obj)
+    rows, is_array = _rows(obj)
     if ext in (".h5", ".hdf5"):
-        try:
-            import tables
-        except ImportError:
-            from .exception import ImproperlyConfigured
-            raise ImproperlyConfigured(
-                "Writing '%s' needs PyTables (as in the reference); it is not installed. "
-                "Use a .npy / .npz path instead." % path)
-        compression = tables.Filters(complevel=9, complib="zlib", shuffle=True)
-        with tables.open_file(path, mode="w") as handle:
-            if square and not isinstance(obj, RaggedArray):
-                arr = np.asarray(obj)
-                atom = tables.Atom.from_dtype(arr.dtype)
-                node = handle.create_carray(where="/", name="array", atom=atom,
-                                            shape=arr.shape, filters=compression)
-                node[:] = arr
-            else:
-                n_zeros = len(str(len(rows))) + 1
-                for i, row in enumerate(rows):
-                    row = np.asarray(row)
-                    atom = tables.Atom.from_dtype(row.dtype)
-                    node = handle.create_carray(
-                        where="/", name="array_" + str(i).zfill(n_zeros), atom=atom,
-                        shape=row.shape, filters=compression)
-                    node[:] = row
-        return
-    if ext == ".npz" or not square or isinstance(obj, RaggedArray):
-        flat = np.concatenate([np.asarray(r).reshape(-1) for r in rows]) if rows else np.zeros(0)
+        n_zeros = 1 if is_array else len(str(len(rows))) + 1
+        h5min.write(path, {tag + "_" + str(i).zfill(n_zeros): np.asarray(r)
+                           for i, r in enumerate(rows)})
+        return path
+    if ext == ".npz" or not is_array:
+        flat = np.concatenate([np.asarray(r) for r in rows]) if rows else np.zeros(0)
         np.savez(path if ext == ".npz" else path + ".npz", data=flat,
                  lengths=np.array([len(r) for r in rows], dtype=np.int64))
-        return
+        return path
     np.save(path, np.asarray(obj))
+    return path
 
 
-def load(path):
-    """Inverse of ``save`` for the .npy / .npz forms (and .h5 when PyTables is present)."""
+def load(path, keys=..., stride=1):
+    """Inverse of ``save``; for `.h5` the semantics of ra.py:114-220: a file with one node
+    gives an ndarray, several nodes give a RaggedArray with one row per node (sorted by
+    name), ``stride`` slices every row, ``keys=None`` reads the old '/array' + '/lengths'
+    layout."""
     import os
+    from .util import h5min
     ext = os.path.splitext(path)[1].lower()
     if ext in (".h5", ".hdf5"):
-        import tables
-        with tables.open_file(path) as handle:
-            names = sorted(n.name for n in handle.list_nodes("/"))
-            if names == ["array"]:
-                return handle.get_node("/array")[:]
-            rows = [handle.get_node("/" + n)[:] for n in names]
-        return RaggedArray(rows)
+        f = h5min.File(path)
+        names = f.keys()
+        if keys is None:
+            if "lengths" in names:
+                return RaggedArray(f["array"].read(), lengths=f["lengths"].read())[::stride]
+            return _native(f["arr_0"].read())[::stride]
+        if keys is Ellipsis:
+            keys = sorted(names)
+        if len(keys) == 1:
+            return _native(f[keys[0]].read())[::1]
+        shapes = [f[k].shape for k in keys]
+        if not all(len(shapes[0]) == len(s) for s in shapes):
+            raise DataInvalid(
+                "Loading a RaggedArray using HDF5 file keys requires that all input arrays "
+                "have the same dimension. Got shapes: %s" % shapes)
+        if not all(shapes[0][1:] == s[1:] for s in shapes):
+            raise DataInvalid(
+                "Loading a RaggedArray using HDF5 file keys requires that all input arrays "
+                "share nonragged dimensions. Got shapes: %s" % shapes)
+        dtypes = [f[k].dtype for k in keys]
+        if not all(dtypes[0] == d for d in dtypes):
+            raise DataInvalid("Can't load keys in %s because the keys didn't have all the "
+                              "same dtype. Keys were: %s" % (dtypes[0], keys))
+        rows = [_native(f[k].read())[::stride] for k in keys]
+        return RaggedArray(np.concatenate(rows), lengths=[len(r) for r in rows], copy=False)
     if ext == ".npz":
         z = np.load(path)
-        return RaggedArray(z["data"], lengths=z["lengths"])
-    return np.load(path)
+        r = RaggedArray(z["data"], lengths=z["lengths"])
+        return r if stride == 1 else RaggedArray([row[::stride] for row in r])
+    return np.load(path)[::stride]
+
+
+def _native(a):
+    return a.astype(a.dtype.newbyteorder("="), copy=False)

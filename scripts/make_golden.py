@@ -2,6 +2,10 @@
 
   frame0_xyz.npy        the reference's RMSD test fixture enspara/test/data/frame0.xtc decoded
                         with oracle/xtc.py (501 frames x 22 atoms, float32 nm)
+  frame0_h5_xyz.npy     enspara/test/data/frame0.h5 ('/coordinates', 501 x 22 x 3 float32; the same
+                        trajectory at 1e-3 nm precision) decoded with enspara_b200/util/h5min.py
+                        -- the fixture of the reference's PAM goldens (test_cluster.py:533-554,
+                        :378-419)
   reference_runs.npz    outputs of the REAL reference package (imported from /root/reference
                         through oracle/refharness.py: its own Python loops + its own Cython
                         libdist; mdtraj.rmsd replaced by the restated RMSD) on seeded inputs.
@@ -32,8 +36,36 @@ def main():
     xyz, *_ = xtc.read_xtc(os.path.join(rh.REFERENCE, "enspara/test/data/frame0.xtc"))
     np.save(os.path.join(GOLDEN, "frame0_xyz.npy"), xyz)
 
+    from enspara_b200.util import h5min
+    xyz_h5 = h5min.read(os.path.join(rh.REFERENCE, "enspara/test/data/frame0.h5"),
+                        "coordinates")
+    assert xyz_h5.shape == (501, 22, 3) and xyz_h5.dtype == np.float32
+    np.save(os.path.join(GOLDEN, "frame0_h5_xyz.npy"), xyz_h5)
+
     kc, km, hy, ut, libdist, mpi = rh.modules()
     out = {}
+
+    # ---- the reference's PAM goldens on frame0.h5 (reference loops + restated md.rmsd) ----
+    Th = od.Trajectory(xyz_h5)
+    r = kc.kcenters(Th, od.rmsd, n_clusters=3)
+    ind, d, a, _ = km._kmedoids_pam_update(Th, od.rmsd, list(r.center_indices),
+                                           r.assignments.copy(), r.distances.copy(),
+                                           random_state=0)
+    assert [int(i) for i in ind] == [298, 44, 341], ind   # enspara/test/test_cluster.py:548
+    out["h5_k3_pam_centers"] = np.array(ind)
+    out["h5_k3_pam_assign"] = a
+    out["h5_k3_pam_dist"] = d
+    r = kc.kcenters(Th, od.rmsd, n_clusters=10)
+    props = [int(np.where(r.assignments == cid)[0][0]) for cid in range(10)]
+    ind, d, a, _ = km._kmedoids_pam_update(Th, od.rmsd, list(r.center_indices),
+                                           r.assignments.copy(), r.distances.copy(),
+                                           proposals=props, random_state=0)
+    # enspara/test/test_cluster.py:410-411 (the MPI test; a single rank sees global indices)
+    assert [int(i) for i in ind] == [0, 37, 400, 105, 12, 327, 242, 346, 42, 3], ind
+    out["h5_k10_pam_proposals"] = np.array(props)
+    out["h5_k10_pam_centers"] = np.array(ind)
+    out["h5_k10_pam_assign"] = a
+    out["h5_k10_pam_dist"] = d
 
     # ---- RMSD path on the reference's fixture (reference loops + restated md.rmsd) --------
     T = od.Trajectory(xyz)

@@ -24,3 +24,10 @@ def golden():
 @pytest.fixture(scope="session")
 def frame0_xyz():
     return np.load(os.path.join(GOLDEN, "frame0_xyz.npy"))
+
+
+@pytest.fixture(scope="session")
+def frame0_h5_xyz():
+    """enspara/test/data/frame0.h5 '/coordinates' (decoded by enspara_b200/util/h5min.py,
+    scripts/make_golden.py): the fixture of the reference's PAM goldens."""
+    return np.load(os.path.join(GOLDEN, "frame0_h5_xyz.npy"))

@@ -101,6 +101,47 @@ def test_rmsd_pam_frame0_matches_reference_run(cuda, frame0_xyz, golden):
     assert len(ctrs) == 3 and ctrs[0].xyz.shape == (1, 22, 3)
 
 
+def test_pam_update_mdtraj_golden(cuda, frame0_h5_xyz, golden):
+    """The reference's own exact RMSD golden, enspara/test/test_cluster.py:533-554: k-centers
+    (k=3) on frame0.h5 then one PAM sweep with seed 0 gives medoids [298, 44, 341], and the
+    sweep's result equals a brute-force assignment to those medoids."""
+    from enspara_b200.cluster import kcenters, kmedoids, util
+    from oracle import distances as od
+    X = od.Trajectory(frame0_h5_xyz)
+    r = kcenters.kcenters(X, "rmsd", n_clusters=3)
+    ind, dists, assig, _ = kmedoids._kmedoids_pam_update(
+        X, "rmsd", r.center_indices, r.assignments, r.distances, random_state=0)
+    assert_array_equal(ind, [298, 44, 341])
+    expect_assig, expect_dists = util.assign_to_nearest_center(
+        X, X[[int(i) for i in ind]], "rmsd")
+    assert_array_equal(np.unique(assig), np.arange(3))
+    assert_array_equal(assig, expect_assig)
+    assert_allclose(dists, expect_dists, atol=1e-6)
+    assert_array_equal(assig, golden["h5_k3_pam_assign"])
+    assert_allclose(dists, golden["h5_k3_pam_dist"], rtol=RTOL, atol=ATOL)
+
+
+def test_pam_update_mpi_mdtraj_golden(cuda, frame0_h5_xyz, golden):
+    """enspara/test/test_cluster.py:378-419 on one rank: k=10, proposals = the first member
+    of every cluster -> medoids [0, 37, 400, 105, 12, 327, 242, 346, 42, 3]."""
+    from enspara_b200.cluster import kcenters, kmedoids, util
+    from oracle import distances as od
+    X = od.Trajectory(frame0_h5_xyz)
+    r = kcenters.kcenters(X, "rmsd", n_clusters=10)
+    props = [int(np.where(r.assignments == cid)[0][0]) for cid in range(10)]
+    assert props == golden["h5_k10_pam_proposals"].tolist()
+    ind, dists, assig, _ = kmedoids._kmedoids_pam_update(
+        X, "rmsd", r.center_indices, r.assignments, r.distances, proposals=props,
+        random_state=0)
+    assert_array_equal(ind, [0, 37, 400, 105, 12, 327, 242, 346, 42, 3])
+    true_assigs, true_dists = util.assign_to_nearest_center(
+        X, X[[int(i) for i in ind]], "rmsd")
+    assert_array_equal(assig, true_assigs)
+    assert_allclose(dists, true_dists, rtol=1e-06, atol=1e-03)
+    assert_array_equal(assig, golden["h5_k10_pam_assign"])
+    assert_allclose(dists, golden["h5_k10_pam_dist"], rtol=RTOL, atol=ATOL)
+
+
 def test_rmsd_hybrid_frame0(cuda, frame0_xyz, golden):
     """enspara/test/test_cluster.py:178-198 + exact comparison with the reference run."""
     from enspara_b200.cluster import hybrid

@@ -48,6 +48,36 @@ def test_khybrid_windows(frame0_xyz):
     assert np.std(r.distances) < 0.019
 
 
+def test_pam_update_mdtraj_golden(frame0_h5_xyz):
+    """test_cluster.py:533-554: k-centers k=3 on frame0.h5, one PAM sweep with seed 0 ->
+    medoids [298, 44, 341]; the sweep's result equals a brute-force assignment.  An exact
+    medoid-index golden of the RMSD path (RMSD arithmetic + tie rules + RNG consumption)."""
+    T = od.Trajectory(frame0_h5_xyz)
+    for metric in (od.rmsd, od.rmsd_f32):
+        r = oc.kcenters(T, metric, n_clusters=3)
+        ind, d, a, _ = oc.pam_update(T, metric, list(r.center_indices), r.assignments.copy(),
+                                     r.distances.copy(), random_state=0)
+        assert_array_equal(ind, [298, 44, 341])
+        ea, ed = oc.assign_to_nearest_center(T, T[[int(i) for i in ind]], metric)
+        assert_array_equal(np.unique(a), np.arange(3))
+        assert_array_equal(a, ea)
+        assert_allclose(d, ed, atol=1e-6)
+
+
+def test_pam_update_mpi_mdtraj_golden(frame0_h5_xyz):
+    """test_cluster.py:378-419 seen from one rank: k-centers k=10 on frame0.h5, proposals =
+    first member of every cluster -> medoids [0, 37, 400, 105, 12, 327, 242, 346, 42, 3]."""
+    T = od.Trajectory(frame0_h5_xyz)
+    r = oc.kcenters(T, od.rmsd, n_clusters=10)
+    props = [int(np.where(r.assignments == cid)[0][0]) for cid in range(10)]
+    ind, d, a, _ = oc.pam_update(T, od.rmsd, list(r.center_indices), r.assignments.copy(),
+                                 r.distances.copy(), proposals=props, random_state=0)
+    assert_array_equal(ind, [0, 37, 400, 105, 12, 327, 242, 346, 42, 3])
+    ea, ed = oc.assign_to_nearest_center(T, T[[int(i) for i in ind]], od.rmsd)
+    assert_array_equal(a, ea)
+    assert_allclose(d, ed, rtol=1e-6, atol=1e-3)
+
+
 def test_blobs_pam_golden(golden):
     """test_cluster.py:507-530: centres [0, 7, 17], PAM result == brute-force assignment."""
     X = golden["blobs_X"]
