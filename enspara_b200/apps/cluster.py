@@ -132,9 +132,14 @@ def process_command_line(argv):
                     "implemented for kmedoids")
     if args.no_reassign and args.subsample == 1:
         logger.warning("When subsampling is 1 (or unspecified), --no-reassign has no effect.")
-    if args.subsample != 1 and not args.no_reassign:
-        logger.warning("Re-assignment of skipped frames is not part of this app here "
-                       "(use the reassign step); proceeding as with --no-reassign.")
+    if args.subsample != 1 and not args.no_reassign and args.features:
+        # the reference can only re-assign trajectory inputs (cluster/util.py:531-534 needs
+        # topologies); with features it would crash after clustering -- say so up front
+        logger.warning("Re-assignment of skipped frames needs trajectory inputs; proceeding "
+                       "as with --no-reassign.")
+        args.no_reassign = True
+    if not args.no_reassign and args.subsample > 1 and mpi.size() > 1:
+        logger.warning("Reassignment is suppressed in MPI mode.")   # apps/cluster.py:266-268
         args.no_reassign = True
     return args
 

@@ -41,7 +41,7 @@ class KCentersEngine:
     #: launches queued between two reads of the state block when a distance cutoff is active
     POLL_EVERY = 32
 
-    def __init__(self, data, metric_kind, comm, exact=True):
+    def __init__(self, data, metric_kind, comm, exact=True, triangle=False):
         self.data = data
         self.kind = metric_kind
         self.comm = comm
@@ -71,6 +71,11 @@ class KCentersEngine:
         self.center_list = None
         self._state_host = torch.empty(64, dtype=torch.uint8).pin_memory()
         self.launches = 0
+        # use_triangle_inequality (kcenters.py:287-296): RMSD only; needs the coordinates of the
+        # centres chosen so far (center_store) and the new centre's distance to each (cc)
+        self.triangle = bool(triangle) and self.is_rmsd and self.exact
+        self.center_store = self.center_store_traces = self.cc = None
+        self._queued = 0            # host upper bound of the number of centres
 
     # -- state ---------------------------------------------------------------------------
     def set_state(self, distances, assignments):
@@ -114,7 +119,16 @@ class KCentersEngine:
             return
         s = stream_ptr()
         d = self.data
-        if self.is_rmsd:
+        if self.is_rmsd and self.triangle:
+            cap = int(self.center_store.shape[0])
+            _lib.call("eb_kcenters_step_rmsd_tri", ptr(d.xyz), ptr(d.traces), self.n, d.n_atoms,
+                      self.shard.offset, ptr(self.cand_all), self.shard.size, ptr(self.dist),
+                      ptr(self.assign), n_clusters_limit, float(cutoff), ptr(self.state),
+                      ptr(self.center_list), ptr(self.partials), ptr(self.cand_out),
+                      ptr(self.center_store), ptr(self.center_store_traces), ptr(self.cc), cap,
+                      int(self._queued), int(n_steps), s)
+            self.launches += n_steps       # plus n_steps small centre-centre launches
+        elif self.is_rmsd:
             _lib.call("eb_kcenters_step_rmsd", ptr(d.xyz), ptr(d.traces), self.n, d.n_atoms,
                       self.shard.offset, ptr(self.cand_all), self.shard.size, ptr(self.dist),
                       ptr(self.assign), n_clusters_limit, float(cutoff), ptr(self.state),
@@ -126,7 +140,9 @@ class KCentersEngine:
                       self.shard.size, ptr(self.dist), ptr(self.assign), n_clusters_limit,
                       float(cutoff), ptr(self.state), ptr(self.center_list),
                       ptr(self.partials), ptr(self.cand_out), int(n_steps), s)
-        self.launches += n_steps
+        if not (self.is_rmsd and self.triangle):
+            self.launches += n_steps
+        self._queued += n_steps
         self._exchange()
 
     def _ensure_center_list(self, capacity):
@@ -135,6 +151,27 @@ class KCentersEngine:
             if self.center_list is not None:
                 new[:self.center_list.numel()].copy_(self.center_list)
             self.center_list = new
+        if self.triangle and (self.center_store is None
+                              or self.center_store.shape[0] < capacity):
+            d = self.data
+            store = torch.zeros((capacity, 3, d.a_pad), dtype=torch.float32, device=self.dev)
+            tr = torch.zeros((capacity,), dtype=torch.float64, device=self.dev)
+            cc = torch.zeros((capacity,), dtype=torch.float32, device=self.dev)
+            if self.center_store is not None:
+                m = int(self.center_store.shape[0])
+                store[:m].copy_(self.center_store)
+                tr[:m].copy_(self.center_store_traces)
+            self.center_store, self.center_store_traces, self.cc = store, tr, cc
+
+    def preload_centers(self, centers_dev):
+        """Warm start in triangle mode: the existing centres (a DeviceTrajectory, in centre-id
+        order) go into the store the pruning test reads."""
+        if not self.triangle:
+            return
+        m = len(centers_dev)
+        self._ensure_center_list(max(m, 1))
+        self.center_store[:m].copy_(centers_dev.xyz[:m])
+        self.center_store_traces[:m].copy_(centers_dev.traces[:m])
 
     def run(self, n_clusters, dist_cutoff, n_existing=0, on_progress=None):
         """Run until the reference's stop rule fires (kcenters.py:217).  ``n_existing`` centres
@@ -156,6 +193,7 @@ class KCentersEngine:
         hard_cap = n_existing + n_global
         capacity = min(limit, hard_cap) if bounded else min(hard_cap, n_existing + 4096)
         self._ensure_center_list(capacity)
+        self._queued = n_existing
         queued = n_existing          # centre ids for which a launch has been queued
         while True:
             if bounded and cutoff <= 0.0:

@@ -145,35 +145,67 @@ def tc_applicable(metric, data, k):
             and len(data) >= 128)
 
 
-def assign_device_tc(metric, data, centers, k=None, stats=None):
-    """Dense nearest-centre pass through the tcgen05 screen + exact re-score
-    (csrc/eb_tc_screen.cu).  Same result as ``assign_device`` (the exact path decides)."""
+def assign_device_tc(metric, data, centers, k=None, stats=None, frame_idx=None, n_idx=None,
+                     out_dist=None, out_assign=None, scatter=False, workspace=None):
+    """Nearest-centre pass through the tcgen05 screen + exact re-score (csrc/eb_tc_screen.cu).
+    Same result as ``assign_device`` (the exact path decides).  ``frame_idx`` (device int64)
+    restricts the pass to a subset; with ``scatter`` the full-length ``out_*`` arrays receive
+    frame f's result at position f (PAM's re-assignment of X[dst_up_assig_this],
+    kmedoids.py:666-667).  ``workspace``: dict reused between calls (scratch buffers)."""
     n = len(data)
     k = len(centers) if k is None else int(k)
     dev = data.xyz.device
     lib = _lib.load()
-    out_dist = torch.full((n,), float("inf"), dtype=torch.float32, device=dev)
-    out_assign = torch.zeros((n,), dtype=torch.int32, device=dev)
-    cand = torch.zeros((n,), dtype=torch.int32, device=dev)
-    chunk = min(n, TC_CHUNK_FRAMES)
-    scratch = torch.empty(int(lib.eb_tc_scratch_bytes(chunk, data.n_atoms, k)),
-                          dtype=torch.uint8, device=dev)
+    m = n if frame_idx is None else int(frame_idx.numel() if n_idx is None else n_idx)
+    if out_dist is None:
+        out_dist = torch.full((m,), float("inf"), dtype=torch.float32, device=dev)
+        out_assign = torch.zeros((m,), dtype=torch.int32, device=dev)
+        scatter = False
+    if m == 0 or k == 0:
+        return out_dist, out_assign
+    ws = workspace if workspace is not None else {}
+    chunk = min(m, TC_CHUNK_FRAMES)
+    need = int(lib.eb_tc_scratch_bytes(chunk, data.n_atoms, k))
+    if ws.get("scratch") is None or ws["scratch"].numel() < need:
+        ws["scratch"] = None
+        ws["scratch"] = torch.empty(need + need // 4, dtype=torch.uint8, device=dev)
+    if ws.get("cand") is None or ws["cand"].numel() < m:
+        ws["cand"] = torch.empty(m + m // 4 + 128, dtype=torch.int32, device=dev)
+    scratch, cand = ws["scratch"], ws["cand"][:m]
     kappa = TC_KAPPA_PER_ATOM * data.a_pad
-    for lo in range(0, n, chunk):
-        hi = min(n, lo + chunk)
-        _lib.call("eb_rmsd_assign_tc", ptr(data.xyz[lo:]), ptr(data.traces[lo:]), hi - lo,
-                  data.n_atoms, ptr(centers.xyz), ptr(centers.traces), k, float(kappa),
-                  ptr(out_dist[lo:]), ptr(out_assign[lo:]), ptr(cand[lo:]), ptr(scratch), None,
-                  1, stream_ptr())
-    overflow = torch.nonzero(cand < 0).view(-1)
+    for lo in range(0, m, chunk):
+        hi = min(m, lo + chunk)
+        if frame_idx is None:
+            _lib.call("eb_rmsd_assign_tc", ptr(data.xyz[lo:]), ptr(data.traces[lo:]), hi - lo,
+                      data.n_atoms, ptr(centers.xyz), ptr(centers.traces), k, float(kappa),
+                      None, 0, ptr(out_dist[lo:]), ptr(out_assign[lo:]), ptr(cand[lo:]),
+                      ptr(scratch), None, 1, stream_ptr())
+        else:
+            od = out_dist if scatter else out_dist[lo:]
+            oa = out_assign if scatter else out_assign[lo:]
+            _lib.call("eb_rmsd_assign_tc", ptr(data.xyz), ptr(data.traces), hi - lo,
+                      data.n_atoms, ptr(centers.xyz), ptr(centers.traces), k, float(kappa),
+                      ptr(frame_idx[lo:]), int(scatter), ptr(od), ptr(oa), ptr(cand[lo:]),
+                      ptr(scratch), None, 1, stream_ptr())
+    overflow = torch.nonzero(cand < 0).view(-1)          # positions within the pass
     if stats is not None:
         stats["survivors_mean"] = float(cand.clamp(min=0).float().mean().cpu())
         stats["overflow_frames"] = int(overflow.numel())
     if overflow.numel() > 0:
         # a candidate list overflowed for these frames: exact pass over all centres
-        assign_device(metric, data, centers, frame_idx=overflow.to(torch.int64).contiguous(),
-                      out_dist=out_dist, out_assign=out_assign, accumulate=False, scatter=True,
-                      k=k)
+        if frame_idx is None:
+            assign_device(metric, data, centers, frame_idx=overflow.to(torch.int64).contiguous(),
+                          out_dist=out_dist, out_assign=out_assign, accumulate=False,
+                          scatter=True, k=k)
+        elif scatter:
+            assign_device(metric, data, centers,
+                          frame_idx=frame_idx[:m][overflow].contiguous(), out_dist=out_dist,
+                          out_assign=out_assign, accumulate=False, scatter=True, k=k)
+        else:
+            d2, a2 = assign_device(metric, data, centers,
+                                   frame_idx=frame_idx[:m][overflow].contiguous(), k=k)
+            out_dist[overflow] = d2
+            out_assign[overflow] = a2
     return out_dist, out_assign
 
 

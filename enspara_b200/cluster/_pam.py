@@ -27,6 +27,9 @@ from ._engine import ShardInfo
 
 
 class PamEngine:
+    #: (frame, medoid) pairs below which the exact kernel is used for the ambiguous subset
+    TC_MIN_PAIRS = 1 << 15
+
     def __init__(self, data, metric, comm, distances, assignments, medoid_global_inds):
         self.data = data
         self.metric = metric
@@ -57,6 +60,10 @@ class PamEngine:
         self.saved = self._fetch_frames([])  # 1-frame scratch: the medoid a proposal displaces
         self.cost_num = self._sumsq(self.dist)
         self.n_global = self.shard.n_global
+        # the ambiguous-subset re-assignment goes through the tcgen05 screen when it applies
+        self.use_tc = self.is_rmsd and _ops.tc_applicable(metric, data, self.k)
+        self._tc_ws = {}
+        self.profile = None
 
     # -- helpers -------------------------------------------------------------------------
     def _to_dev(self, arr, dtype):
@@ -151,15 +158,30 @@ class PamEngine:
                 self.comm.broadcast(self.prop.X, owner)
 
     # -- one sweep -----------------------------------------------------------------------
-    def sweep(self, proposals=None, random_state=None, striped_randind=False, log=None):
+    def sweep(self, proposals=None, random_state=None, striped_randind=False, log=None,
+              max_proposals=None):
         """One pass over all k clusters (kmedoids.py:609-694).  ``proposals``: GLOBAL frame
-        indices, one per cluster, or None for random proposals.  Returns acceptances."""
+        indices, one per cluster, or None for random proposals.  Returns acceptances.
+        ``max_proposals`` stops after that many clusters (benchmarks only)."""
         rs = check_random_state(random_state)
         sh = self.shard
         acceptances = 0
+        prof = self.profile          # None, or dict phase -> seconds (developer timing)
+
+        def tick(name, t0):
+            if prof is None:
+                return 0.0
+            torch.cuda.synchronize()
+            import time as _t
+            now = _t.perf_counter()
+            if name:
+                prof[name] = prof.get(name, 0.0) + now - t0
+            return now
+        t = tick(None, 0.0)
         if proposals is None:
             self._refresh_counts()
-        for cid in range(self.k):
+        t = tick("counts", t)
+        for cid in range(self.k if max_proposals is None else min(self.k, max_proposals)):
             # ---- proposal (kmedoids.py:616-628, 482-517) -------------------------------
             if proposals is None:
                 n_states = self._member_counts(cid)
@@ -186,9 +208,11 @@ class PamEngine:
                 owner, loc = sh.to_rank_local(prop_global)
                 self._load_proposal(owner, local_idx=loc)
 
+            t = tick("proposal", t)
             # ---- full pass + three-way split (kmedoids.py:637-658) -------------------
             d = _ops.one_to_all_device(self.metric, self.data, self.prop,
                                        center_trace_dev=True, out=self.new_ctr_dist)
+            t = tick("full_pass", t)
             _lib.call("eb_pam_classify", ptr(d), ptr(self.dist), ptr(self.assign), self.n,
                       int(not self.is_rmsd), cid, ptr(self.new_dist), ptr(self.new_assign),
                       ptr(self.ambig_idx), ptr(self.scal_i[1:]), stream_ptr())
@@ -198,15 +222,26 @@ class PamEngine:
                 mine = int(scal[0]) + sh.offset if sh.rank == owner else -1
                 prop_global = max(self.comm.all_gather_object(mine)) if sh.size > 1 else mine
 
+            t = tick("classify+readback", t)
             # ---- ambiguous frames against all medoids, proposal in slot cid (:660-670) --
             self._slot_copy(self.saved, 0, self.medoids, cid)
             self._slot_copy(self.medoids, cid, self.prop, 0)
             if n_ambig > 0:
-                _ops.assign_device(self.metric, self.data, self.medoids,
-                                   frame_idx=self.ambig_idx, n_idx=n_ambig,
-                                   out_dist=self.new_dist, out_assign=self.new_assign,
-                                   accumulate=False, scatter=True, k=self.k)
+                if self.use_tc and n_ambig * self.k >= self.TC_MIN_PAIRS:
+                    # tensor-core screen + exact re-score: same result as the exact kernel
+                    _ops.assign_device_tc(self.metric, self.data, self.medoids, k=self.k,
+                                          frame_idx=self.ambig_idx, n_idx=n_ambig,
+                                          out_dist=self.new_dist, out_assign=self.new_assign,
+                                          scatter=True, workspace=self._tc_ws)
+                else:
+                    _ops.assign_device(self.metric, self.data, self.medoids,
+                                       frame_idx=self.ambig_idx, n_idx=n_ambig,
+                                       out_dist=self.new_dist, out_assign=self.new_assign,
+                                       accumulate=False, scatter=True, k=self.k)
 
+            t = tick("subset_assign", t)
+            if prof is not None:
+                prof["n_ambig"] = prof.get("n_ambig", 0) + n_ambig
             # ---- accept / reject on mean-square cost (kmedoids.py:680-694) -----------------
             new_num = self._sumsq(self.new_dist)
             old_cost = self.cost_num / self.n_global
@@ -224,6 +259,7 @@ class PamEngine:
                     self._refresh_counts()
             else:
                 self._slot_copy(self.medoids, cid, self.saved, 0)
+            t = tick("cost+accept", t)
         self.last_cost = self.cost_num / self.n_global
         return acceptances
 

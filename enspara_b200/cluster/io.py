@@ -160,14 +160,25 @@ def write_centers(result, args, intermediate_n=None):
 
 
 def write_assignments_and_distances(result, args, intermediate_n=None):
-    """util.py:511-549 for subsample == 1 (re-assignment of skipped frames is the `reassign`
-    app's job)."""
+    """util.py:511-549: subsample == 1 writes the clustering's own arrays; otherwise every
+    frame of the input trajectories is re-assigned to the centres found on the subsample
+    (streamed through cluster/reassign.py) unless --no-reassign."""
     dpath, apath = args.distances, args.assignments
     if intermediate_n is not None:
         dpath = _intermediate_path(dpath, intermediate_n)
         apath = _intermediate_path(apath, intermediate_n)
-    ra.save(dpath, result.distances)
-    ra.save(apath, result.assignments)
+    if args.subsample == 1:
+        ra.save(dpath, result.distances)
+        ra.save(apath, result.assignments)
+    elif not args.no_reassign:
+        from .reassign import reassign
+        logger.debug("Reassigning data from subsampling of %s", args.subsample)
+        assig, dist = reassign(args.topologies, args.trajectories, args.atoms,
+                               centers=result.centers)
+        ra.save(dpath, dist)
+        ra.save(apath, assig)
+    else:
+        logger.debug("Got --no-reassign, not doing reassigment")
 
 
 def write_intermediate(result, args, lengths, tag):

@@ -89,10 +89,12 @@ def kcenters(traj, distance_method, n_clusters=np.inf, dist_cutoff=0, init_cente
     cover this rank's frames and centre indices are ``(owner_rank, local_index)`` pairs
     (kcenters.py:375-376).
 
-    ``use_triangle_inequality`` is accepted for API compatibility; it only prunes work in the
-    reference and never changes results (test_cluster.py:710-770), and the fused kernel always
-    evaluates every frame.  ``exact=False`` selects the float32-block accumulation mode of the
-    kernel (faster, ~1e-5 relative).
+    ``use_triangle_inequality`` (kcenters.py:287-296): frames whose distance to their centre is
+    at most half the distance between that centre and the new one are not re-evaluated -- on
+    the GPU they are not even read, which removes most of the HBM traffic once there are many
+    centres.  Results are the same as without it (test_cluster.py:710-770).  RMSD only; feature
+    metrics always evaluate every row.  ``exact=False`` selects the float32-block accumulation
+    mode of the kernel (~1e-5 relative).
     """
     if (n_clusters is np.inf) and (dist_cutoff == 0):
         raise ImproperlyConfigured("Either n_clusters or cluster_radius "
@@ -113,7 +115,8 @@ def kcenters(traj, distance_method, n_clusters=np.inf, dist_cutoff=0, init_cente
 
     data = metric.to_device(traj)
     comm = mpi.comm if mpi_mode else _SingleComm()
-    engine = KCentersEngine(data, metric.kind, comm, exact=exact)
+    engine = KCentersEngine(data, metric.kind, comm, exact=exact,
+                            triangle=use_triangle_inequality)
 
     centers = []
     ctr_inds = []
@@ -128,6 +131,12 @@ def kcenters(traj, distance_method, n_clusters=np.inf, dist_cutoff=0, init_cente
         a_host, d_host = engine.results_host()
         ctr_inds = list(util.find_cluster_centers(a_host, d_host))
         n_existing = len(ctr_inds)
+        if n_existing == len(centers):
+            engine.preload_centers(cdev)
+        else:
+            # an initial centre without members: new centre ids would collide with the ids of
+            # the supplied centres (a reference quirk); prune nothing rather than prune wrongly
+            engine.triangle = False
 
     new_global, maxdist = engine.run(n_clusters, dist_cutoff, n_existing=n_existing)
 

@@ -126,7 +126,10 @@ constexpr int kStepThreads = 256;
 constexpr int kStepWarps = kStepThreads / 32;
 constexpr int kSumStride = 9;  // doubles per frame slot; odd -> conflict-free 64-bit reads
 
-enum StepMode { kModeStep = 0, kModeSeed = 1, kModeDistOnly = 2 };
+enum StepMode { kModeStep = 0, kModeSeed = 1, kModeDistOnly = 2, kModeCC = 3 };
+// VAR: 0 default, 1/2 developer load variants, 3 = triangle-inequality pruning
+// (kcenters.py:287-296): frames with dist <= d(new centre, their centre) / 2 are not streamed.
+constexpr int kVarTri = 3;
 
 struct StepSmem {
     Partial red[32];
@@ -144,7 +147,8 @@ k_kcenters_step_rmsd(const float *__restrict__ xyz, const double *__restrict__ t
                      int n_cand, size_t rec_bytes, float *dist, int *assign,
                      int n_clusters_limit, double cutoff, eb_kc_state *state,
                      int64_t *center_list, Partial *partials, unsigned char *cand_out,
-                     const float *center_direct, const double *center_trace_direct, float *out_only)
+                     const float *center_direct, const double *center_trace_direct, float *out_only,
+                     float *cstore, double *cstore_traces, const float *__restrict__ cc)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StepSmem *ss = reinterpret_cast<StepSmem *>(smem_raw);
@@ -159,14 +163,14 @@ k_kcenters_step_rmsd(const float *__restrict__ xyz, const double *__restrict__ t
     double Gb = 0.0;
     CenterSmem cs = center_smem_carve(center_base, A4);
 
-    if (MODE == kModeStep) {
+    if (MODE == kModeStep || MODE == kModeCC) {
         // ---- prologue: winner among the gathered candidates, stop rule -------------------
         double cd;
         int64_t ci;
         const int r = pick_candidate(cand_in, n_cand, rec_bytes, cd, ci);
         const bool active = (r >= 0) && step_active(state, n_clusters_limit, cd, cutoff, k);
         if (!active) {
-            if (blockIdx.x == 0 && threadIdx.x == 0) {
+            if (MODE == kModeStep && blockIdx.x == 0 && threadIdx.x == 0) {
                 if (!state->done) {
                     state->done = 1;
                     state->maxdist = cd;
@@ -182,6 +186,17 @@ k_kcenters_step_rmsd(const float *__restrict__ xyz, const double *__restrict__ t
         if (threadIdx.x == 0) {
             ss->center_index = ci;
             ss->maxdist = cd;
+        }
+        if (MODE == kModeCC) {
+            // distances from the new centre to the k centres chosen so far (the stored copies
+            // are this launch's "frames"), and the new centre joins the store at slot k
+            n = k;
+            if (blockIdx.x == 0) {
+                const float4 *src = reinterpret_cast<const float4 *>(rec + sizeof(RecHeader));
+                float4 *dst = reinterpret_cast<float4 *>(cstore + (size_t)k * 3 * A_pad);
+                for (int t = threadIdx.x; t < 3 * A4; t += blockDim.x) dst[t] = __ldcg(src + t);
+                if (threadIdx.x == 0) cstore_traces[k] = Gb;
+            }
         }
         __syncthreads();
     } else if (MODE == kModeDistOnly) {
@@ -200,24 +215,39 @@ k_kcenters_step_rmsd(const float *__restrict__ xyz, const double *__restrict__ t
     for (long chunk = (long)blockIdx.x * kStepWarps + warp; chunk < n_chunks;
          chunk += warps_total) {
         const long base = chunk << 5;
+        const long f = base + lane;
+        // triangle-inequality pruning: lane l decides for frame base + l, the warp shares the
+        // decisions as a bit mask; rounds whose four frames are all pruned load nothing
+        unsigned need_mask = 0xffffffffu;
+        float tri_old = 0.f;
+        if (VAR == kVarTri && MODE == kModeStep) {
+            bool need = false;
+            if (f < n) {
+                tri_old = dist[f];
+                const int a = assign[f];
+                need = (a < 0) || (tri_old > 0.5f * __ldg(cc + a));   // kcenters.py:289
+            }
+            need_mask = __ballot_sync(0xffffffffu, need);
+        }
         if (MODE != kModeSeed) {
 #pragma unroll 1
             for (int s = 0; s < 8; ++s) {
-                const long f = base + 4 * s + g;
+                if (VAR == kVarTri && ((need_mask >> (4 * s)) & 0xfu) == 0u) continue;
+                const long fs = base + 4 * s + g;
                 double m[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
                 if (VAR == 2) {
                     // software prefetch of the frame this group streams in the next round
                     // (or the first round of the warp's next chunk) into L2
-                    const long fn = (s < 7) ? f + 4 : ((chunk + warps_total) << 5) + g;
+                    const long fn = (s < 7) ? fs + 4 : ((chunk + warps_total) << 5) + g;
                     if (fn < n) {
                         const char *pn = reinterpret_cast<const char *>(xyz + (size_t)fn * 3 * A_pad);
                         const int n_lines = (12 * A_pad + 127) >> 7;
                         for (int l = l8; l < n_lines; l += 8) prefetch_l2(pn + ((size_t)l << 7));
                     }
                 }
-                if (f < n)
+                if (fs < n && (VAR != kVarTri || ((need_mask >> (4 * s + g)) & 1u)))
                     frame_inner_products<EXACT, (VAR == 1 ? 1 : 0)>(
-                        m, xyz + (size_t)f * 3 * A_pad, A4, l8, cs);
+                        m, xyz + (size_t)fs * 3 * A_pad, A4, l8, cs);
                 group8_reduce(m);
                 if (l8 == 0) {
                     double *dst = my_sums + (4 * s + g) * kSumStride;
@@ -227,18 +257,19 @@ k_kcenters_step_rmsd(const float *__restrict__ xyz, const double *__restrict__ t
             }
             __syncwarp();
         }
-        const long f = base + lane;
         if (f < n) {
             double cur;
             if (MODE == kModeSeed) {
                 cur = (double)dist[f];
+            } else if (VAR == kVarTri && MODE == kModeStep && !((need_mask >> lane) & 1u)) {
+                cur = (double)tri_old;     // pruned: distance and assignment stay
             } else {
                 double m[9];
                 const double *src = my_sums + lane * kSumStride;
 #pragma unroll
                 for (int e = 0; e < 9; ++e) m[e] = src[e];
                 const float d = rmsd_from_msd(qcp_msd(m, traces[f], Gb, A));
-                if (MODE == kModeDistOnly) {
+                if (MODE == kModeDistOnly || MODE == kModeCC) {
                     out_only[f] = d;
                     cur = 0.0;
                 } else {
@@ -257,7 +288,7 @@ k_kcenters_step_rmsd(const float *__restrict__ xyz, const double *__restrict__ t
         }
         if (MODE != kModeSeed) __syncwarp();
     }
-    if (MODE == kModeDistOnly) return;
+    if (MODE == kModeDistOnly || MODE == kModeCC) return;
 
     // ---- epilogue: shard arg-max, candidate record, centre list ----------------------------
     if (!grid_argmax_last_block(best_d, best_i, partials, state, ss->red, &ss->flag)) return;
@@ -319,13 +350,21 @@ static int k1_variant()
     return v;
 }
 
+// optional extras of a launch: the centre store + centre-centre distances of the triangle mode
+struct StepExtra {
+    float *cstore = nullptr;
+    double *cstore_traces = nullptr;
+    float *cc = nullptr;
+    long grid_frames = -1;   // size the grid for this many frames instead of n (kModeCC)
+};
+
 template <bool EXACT, int MODE, int VAR>
 static int launch_step_v(const float *xyz, const double *traces, long n, int A, long frame_offset,
                        const void *cand_in, int n_cand, float *dist, int *assign,
                        int n_clusters_limit, double cutoff, eb_kc_state *state,
                        int64_t *center_list, void *partials, void *cand_out,
                        const float *center_direct, const double *center_trace_direct,
-                       float *out_only, cudaStream_t stream)
+                       float *out_only, cudaStream_t stream, StepExtra ex = StepExtra())
 {
     const int A_pad = rmsd_apad(A);
     const size_t smem = step_smem_bytes(A_pad);
@@ -340,10 +379,11 @@ static int launch_step_v(const float *xyz, const double *traces, long n, int A, 
         configured = smem;
     }
     const size_t rec_bytes = sizeof(RecHeader) + sizeof(float) * 3 * (size_t)A_pad;
-    kern<<<step_grid(n), kStepThreads, smem, stream>>>(
+    kern<<<step_grid(ex.grid_frames >= 0 ? ex.grid_frames : n), kStepThreads, smem, stream>>>(
         xyz, traces, n, A, A_pad, frame_offset, (const unsigned char *)cand_in, n_cand, rec_bytes,
         dist, assign, n_clusters_limit, cutoff, state, center_list, (Partial *)partials,
-        (unsigned char *)cand_out, center_direct, center_trace_direct, out_only);
+        (unsigned char *)cand_out, center_direct, center_trace_direct, out_only, ex.cstore,
+        ex.cstore_traces, ex.cc);
     EB_LAUNCH_CHECK();
     return EB_OK;
 }
@@ -450,6 +490,48 @@ int eb_kcenters_step_rmsd(const float *xyz_soa, const double *traces, int64_t n,
                                                   dist_cutoff, state, center_list, partials,
                                                   cand_out, nullptr, nullptr, nullptr,
                                                   (cudaStream_t)stream);
+        if (rc != EB_OK) return rc;
+    }
+    return EB_OK;
+}
+
+// Triangle-inequality variant (kcenters.py:287-296, `use_triangle_inequality=True`): per
+// iteration one small launch computes the distances from the new centre to all stored centres
+// (and stores the new centre), then the step skips every frame whose current distance is at
+// most half the distance between its centre and the new one.  Same results as the plain step.
+int eb_kcenters_step_rmsd_tri(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
+                              int64_t frame_offset, const void *cand_in, int n_cand, float *dist,
+                              int32_t *assign, int32_t n_clusters_limit, double dist_cutoff,
+                              eb_kc_state *state, int64_t *center_list, void *partials,
+                              void *cand_out, float *center_store, double *center_store_traces,
+                              float *cc, int64_t store_capacity, int64_t k_upper, int n_steps,
+                              void *stream)
+{
+    EB_CHECK_ARG(n >= 0 && n_atoms > 0, "kcenters_step_rmsd_tri: bad shape");
+    EB_CHECK_ARG(n_steps >= 1, "kcenters_step_rmsd_tri: n_steps < 1");
+    EB_CHECK_ARG(n_steps == 1 || (n_cand == 1 && cand_in == cand_out),
+                 "kcenters_step_rmsd_tri: n_steps > 1 needs a single shard");
+    EB_CHECK_ARG(n_cand >= 1 && cand_in && cand_out && state && partials && center_list &&
+                     center_store && center_store_traces && cc,
+                 "kcenters_step_rmsd_tri: null pointer / n_cand < 1");
+    EB_CHECK_ARG(k_upper >= 0 && k_upper + n_steps <= store_capacity,
+                 "kcenters_step_rmsd_tri: centre store too small");
+    for (int it = 0; it < n_steps; ++it) {
+        StepExtra ex;
+        ex.cstore = center_store;
+        ex.cstore_traces = center_store_traces;
+        ex.grid_frames = k_upper + it;          // host-side upper bound of the centre count
+        int rc = launch_step_v<true, kModeCC, 0>(
+            center_store, center_store_traces, 0, n_atoms, 0, cand_in, n_cand, nullptr, nullptr,
+            n_clusters_limit, dist_cutoff, state, nullptr, nullptr, nullptr, nullptr, nullptr, cc,
+            (cudaStream_t)stream, ex);
+        if (rc != EB_OK) return rc;
+        StepExtra ex2;
+        ex2.cc = cc;
+        rc = launch_step_v<true, kModeStep, kVarTri>(
+            xyz_soa, traces, n, n_atoms, frame_offset, cand_in, n_cand, dist, assign,
+            n_clusters_limit, dist_cutoff, state, center_list, partials, cand_out, nullptr,
+            nullptr, nullptr, (cudaStream_t)stream, ex2);
         if (rc != EB_OK) return rc;
     }
     return EB_OK;

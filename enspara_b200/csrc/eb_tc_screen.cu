@@ -16,7 +16,7 @@
 // (3xTF32).  Operands are pre-split AND pre-packed by k_pack_tf32 into the exact swizzled
 // shared-memory image of every tile (64-byte rows, SWIZZLE_64B), so one pipeline stage arrives
 // with two contiguous bulk copies (cp.async.bulk) in a 3-stage mbarrier ring; one elected thread issues
-// tcgen05.mma.kind::tf32 (M=128 frames, N=96 = 32 centres x 3), 9 MMAs per 8 atoms.
+// tcgen05.mma.kind::tf32 (M=128 frames, N=144 = 48 centres x 3), 9 MMAs per 8 atoms.
 //
 // Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2-5
 // epilogue (TMEM lane quarter = warp_id % 4).
@@ -27,19 +27,23 @@ namespace eb {
 namespace tc {
 
 constexpr int BM = 128;                  // frames per tile  (= TMEM lanes)
-constexpr int NC = 32;                   // centres per tile
+constexpr int NC = 48;                   // centres per tile
 constexpr int BN = 3 * NC;               // B rows per tile: (centre, coordinate)
 constexpr int BK = 16;                   // atoms per stage: 64-byte rows
 constexpr int STAGES = 3;
 constexpr int A_TILE = BM * BK * 4;      // 8192
 constexpr int B_TILE = BN * BK * 4;      // 6144
 constexpr int STAGE_BYTES = 6 * A_TILE + 2 * B_TILE;  // {hi,lo} x 3 coords of A, {hi,lo} of B
-constexpr int TMEM_COLS = 512;           // 3 accumulators x 96 columns = 288 -> power of two
+constexpr int TMEM_COLS = 512;           // 3 accumulators x 144 columns = 432 -> power of two
 constexpr int THREADS = 64 + 128 * 2;  // producer, MMA, 8 epilogue warps
 constexpr int MAX_CAND = 32;   // survivors kept per candidate list
-constexpr int MAX_SEG = 4;     // centre segments: CTAs sharing a frame tile hit it in L2
-constexpr int EPI_HALVES = 2;  // two epilogue warps per TMEM lane quarter, 16 centres each
-constexpr int MAX_LISTS = MAX_SEG * EPI_HALVES;  // candidate lists per frame
+constexpr int DEF_SEG = 4;     // centre segments: CTAs sharing a frame tile hit it in L2
+constexpr int MAX_SEG = 32;    // small frame subsets (PAM) are spread over more segments
+constexpr int EPI_HALVES = 2;  // two epilogue warps per TMEM lane quarter, NC/2 centres each
+constexpr int GROUPS_PER_HALF = NC / 8 / EPI_HALVES;  // groups of 8 centres per epilogue warp
+static_assert(NC % (8 * EPI_HALVES) == 0, "centre tile must split into groups of 8 per half");
+static_assert(3 * BN <= TMEM_COLS, "three accumulators must fit TMEM");
+static_assert(BN % 16 == 0 && BN <= 256, "UMMA N constraint for M = 128");
 
 // ---- operand split + packing -----------------------------------------------------------------
 // Writes, for every (tile T, k-block kb, sub-row-set s, hi|lo), the exact shared-memory image of
@@ -48,10 +52,11 @@ constexpr int MAX_LISTS = MAX_SEG * EPI_HALVES;  // candidate lists per frame
 // with ONE bulk copy instead of hundreds of 64-byte TMA row requests.
 //   image index = (((T * KB + kb) * S + s) * 2 + hl) * (RT * 64 bytes)
 //   source row  = (T * RT + r) * S + s   of the (rows_total x A_pad) float matrix `x`
-// Frames: RT = 128, S = 3 (the three coordinate rows of a frame); centres: RT = 96, S = 1.
+// Frames: RT = 128, S = 3 (the three coordinate rows of a frame); centres: RT = 144, S = 1.
+// `row_idx` (optional, frames only): tile row (T*RT + r) is frame row_idx[T*RT + r] of `x`.
 __global__ void __launch_bounds__(256)
 k_pack_tf32(const float *__restrict__ x, long rows_total, int A_pad, int RT, int S, long n_tiles,
-            unsigned char *__restrict__ img)
+            const int64_t *__restrict__ row_idx, unsigned char *__restrict__ img)
 {
     const int Q = A_pad >> 2;  // float4 per row
     const int KB = A_pad / BK;
@@ -66,7 +71,10 @@ k_pack_tf32(const float *__restrict__ x, long rows_total, int A_pad, int RT, int
         const long T = tr / RT;
         const int r = (int)(tr - T * RT);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (rr < rows_total) v = __ldg(reinterpret_cast<const float4 *>(x + (size_t)rr * A_pad) + q);
+        if (rr < rows_total) {
+            const long src = row_idx ? (long)__ldg(row_idx + tr) * S + sidx : rr;
+            v = __ldg(reinterpret_cast<const float4 *>(x + (size_t)src * A_pad) + q);
+        }
         float4 h, l;
         h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
         h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
@@ -193,7 +201,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 k_tc_screen(const unsigned char *__restrict__ a_img, const unsigned char *__restrict__ b_img,
             const double *__restrict__ traces, const double *__restrict__ ctraces, long n, int k,
             int n_atoms, int A_pad, double kappa, float *dbg, int *cand_count, int *cand_list,
-            float *cand_bound, float *cand_umin, int n_seg)
+            float *cand_bound, float *cand_umin, int n_seg, const int64_t *__restrict__ frame_idx)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *tiles = smem_raw;
@@ -313,7 +321,7 @@ k_tc_screen(const unsigned char *__restrict__ a_img, const unsigned char *__rest
             const int ct_hi = min(n_ct, (seg + 1) * ct_per_seg);
             const long f = ft * BM + row;
             const bool fvalid = f < n;
-            const double Ga = fvalid ? traces[f] : 0.0;
+            const double Ga = fvalid ? traces[frame_idx ? frame_idx[f] : f] : 0.0;
             const float sa = sqrtf((float)Ga);
             // screen state of this (frame, list): thread-private across the centre tiles; all
             // bounds are kept in units of N * msd
@@ -327,8 +335,8 @@ k_tc_screen(const unsigned char *__restrict__ a_img, const unsigned char *__rest
                 tc_fence_after();
                 const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-                for (int gg = 0; gg < 2; ++gg) {   // 8 centres = 24 columns per accumulator
-                    const int g = hh * 2 + gg;
+                for (int gg = 0; gg < GROUPS_PER_HALF; ++gg) {   // 8 centres = 24 columns
+                    const int g = hh * GROUPS_PER_HALF + gg;
                     float m[3][24];
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
@@ -457,7 +465,8 @@ k_rescore(const float *__restrict__ xyz, const double *__restrict__ traces, long
           int A_pad, const float *__restrict__ centers, const double *__restrict__ ctraces,
           const int *__restrict__ cand_count, const int *__restrict__ cand_list,
           const float *__restrict__ cand_bound, const float *__restrict__ cand_umin, int n_seg,
-          float *out_dist, int *out_assign, int *frame_flag)
+          float *out_dist, int *out_assign, int *frame_flag,
+          const int64_t *__restrict__ frame_idx, int scatter)
 {
     const int lane = threadIdx.x & 31, g = lane >> 3, l8 = lane & 7;
     const int A4 = A_pad >> 2;
@@ -481,7 +490,8 @@ k_rescore(const float *__restrict__ xyz, const double *__restrict__ traces, long
         }
         float best_d = INFINITY;
         int best_c = 0, evaluated = 0;
-        const float4 *px = reinterpret_cast<const float4 *>(xyz + (size_t)(valid ? f : 0) * stride);
+        const long src = valid ? (frame_idx ? (long)frame_idx[f] : f) : 0;  // row of xyz / traces
+        const float4 *px = reinterpret_cast<const float4 *>(xyz + (size_t)src * stride);
         for (int sgm = 0; sgm < n_seg; ++sgm) {
             const int cnt = (valid && !overflow) ? cand_count[(size_t)f * n_seg + sgm] : 0;
             int cnt_max = cnt;
@@ -507,7 +517,7 @@ k_rescore(const float *__restrict__ xyz, const double *__restrict__ traces, long
                 }
                 group8_reduce(m);
                 if (act) {
-                    const float d = rmsd_from_msd(qcp_msd(m, traces[f], ctraces[c], n_atoms));
+                    const float d = rmsd_from_msd(qcp_msd(m, traces[src], ctraces[c], n_atoms));
                     ++evaluated;
                     // lists are not globally ordered by centre: lowest centre index on exact
                     // ties, which is what strict '<' in centre order gives (util.py:201)
@@ -523,8 +533,9 @@ k_rescore(const float *__restrict__ xyz, const double *__restrict__ traces, long
                 frame_flag[f] = -1;  // the host sends this frame through the exact kernel
             } else {
                 frame_flag[f] = evaluated;
-                out_dist[f] = best_d;
-                out_assign[f] = best_c;
+                const long o = scatter ? src : f;
+                out_dist[o] = best_d;
+                out_assign[o] = best_c;
             }
         }
         (void)total;
@@ -536,26 +547,50 @@ k_rescore(const float *__restrict__ xyz, const double *__restrict__ traces, long
 
 using namespace eb;
 
+// Centre segments per frame tile: the default keeps consecutive CTAs on one frame tile (its A
+// operand is then served by L2); a small frame subset (PAM's ambiguous frames) is cut into more
+// segments so that every SM gets a work item.
+static int tc_pick_nseg(long n_ft, int n_ct)
+{
+    int n_seg = n_ct < tc::DEF_SEG ? n_ct : tc::DEF_SEG;
+    const long want = 2L * sm_count();
+    if (n_ft * n_seg < want) {
+        long s2 = (want + n_ft - 1) / n_ft;
+        if (s2 > tc::MAX_SEG) s2 = tc::MAX_SEG;
+        if (s2 > n_ct) s2 = n_ct;
+        if (s2 > n_seg) n_seg = (int)s2;
+    }
+    return n_seg < 1 ? 1 : n_seg;
+}
+
 extern "C" {
 
 size_t eb_tc_scratch_bytes(int64_t n, int n_atoms, int32_t k)
 {
     const size_t row = sizeof(float) * 3 * (size_t)rmsd_apad(n_atoms);
+    const long n_ft = (n + tc::BM - 1) / tc::BM;
+    const int n_ct = (k + tc::NC - 1) / tc::NC;
+    const size_t n_lists = (size_t)tc_pick_nseg(n_ft < 1 ? 1 : n_ft, n_ct < 1 ? 1 : n_ct) *
+                           tc::EPI_HALVES;
     // split copies of frames and centres + candidate lists
     return 2 * row * (size_t)(n + tc::BM) + 2 * row * (size_t)(k + tc::NC) +
-           (size_t)n * tc::MAX_LISTS *
+           (size_t)n * n_lists *
                (sizeof(int) + sizeof(float) + tc::MAX_CAND * (sizeof(int) + sizeof(float))) +
            4096;
 }
 
 // mode 0 (debug): dbg receives the approximate inner-product matrices, n x k x 9 floats.
 // mode 1: screen + exact re-score.  out_dist/out_assign get the exact result for every frame whose
-//         candidate list did not overflow; n_overflow (device int) counts the others, whose
-//         cand_count is -1 and which the caller must send through eb_rmsd_assign.
+//         candidate list did not overflow; the others have cand_count[i] == -1 and the caller
+//         must send them through eb_rmsd_assign.
+// frame_idx (optional, int64[n]): the pass covers frames frame_idx[0..n) of xyz_soa / traces;
+//         cand_count is indexed by position i; results go to position i, or to frame_idx[i]
+//         when `scatter` is set.
 int eb_rmsd_assign_tc(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
                       const float *centers_soa, const double *center_traces, int32_t k,
-                      double kappa, float *out_dist, int32_t *out_assign, int32_t *cand_count,
-                      void *scratch, float *dbg, int mode, void *stream)
+                      double kappa, const int64_t *frame_idx, int scatter, float *out_dist,
+                      int32_t *out_assign, int32_t *cand_count, void *scratch, float *dbg,
+                      int mode, void *stream)
 {
     EB_CHECK_ARG(n >= 0 && n_atoms > 0 && k >= 0, "rmsd_assign_tc: bad shape");
     if (n == 0 || k == 0) return EB_OK;
@@ -573,30 +608,30 @@ int eb_rmsd_assign_tc(const float *xyz_soa, const double *traces, int64_t n, int
     unsigned char *b_img = a_img + 2 * sizeof(float) * row * a_rows;
     unsigned char *lists = b_img + 2 * sizeof(float) * row * c_rows;
     const int n_ct_total = (k + tc::NC - 1) / tc::NC;
-    const int n_seg = n_ct_total < tc::MAX_SEG ? n_ct_total : tc::MAX_SEG;
+    const long n_ft = (n + tc::BM - 1) / tc::BM;
+    const int n_seg = tc_pick_nseg(n_ft, n_ct_total);
+    const size_t n_lists = (size_t)n_seg * tc::EPI_HALVES;
     int *cand_list = (int *)lists;
-    float *cand_bound = (float *)(cand_list + (size_t)n * tc::MAX_LISTS * tc::MAX_CAND);
-    float *cand_umin = cand_bound + (size_t)n * tc::MAX_LISTS * tc::MAX_CAND;
-    int *seg_count = (int *)(cand_umin + (size_t)n * tc::MAX_LISTS);
+    float *cand_bound = (float *)(cand_list + (size_t)n * n_lists * tc::MAX_CAND);
+    float *cand_umin = cand_bound + (size_t)n * n_lists * tc::MAX_CAND;
+    int *seg_count = (int *)(cand_umin + (size_t)n * n_lists);
 
     {
-        const long a_tiles = (n + tc::BM - 1) / tc::BM;
-        long total = a_tiles * tc::BM * 3 * (long)(A_pad / 4);
+        long total = n_ft * tc::BM * 3 * (long)(A_pad / 4);
         long blocks = (total + 255) / 256;
         if (blocks > 32L * sm_count()) blocks = 32L * sm_count();
-        tc::k_pack_tf32<<<(int)blocks, 256, 0, s>>>(xyz_soa, 3L * n, A_pad, tc::BM, 3, a_tiles,
-                                                    a_img);
+        tc::k_pack_tf32<<<(int)blocks, 256, 0, s>>>(xyz_soa, 3L * n, A_pad, tc::BM, 3, n_ft,
+                                                    frame_idx, a_img);
         EB_LAUNCH_CHECK();
-        const long b_tiles = (k + tc::NC - 1) / tc::NC;
+        const long b_tiles = n_ct_total;
         total = b_tiles * tc::BN * (long)(A_pad / 4);
         blocks = (total + 255) / 256;
         if (blocks > 32L * sm_count()) blocks = 32L * sm_count();
         tc::k_pack_tf32<<<(int)blocks, 256, 0, s>>>(centers_soa, 3L * k, A_pad, tc::BN, 1, b_tiles,
-                                                    b_img);
+                                                    nullptr, b_img);
         EB_LAUNCH_CHECK();
     }
     const size_t smem = (size_t)tc::STAGES * tc::STAGE_BYTES + sizeof(tc::Smem) + 1024;
-    const long n_ft = (n + tc::BM - 1) / tc::BM;
     const long n_items = n_ft * n_seg;
     const int grid = (int)(n_items < sm_count() ? n_items : sm_count());
     if (mode == 0) {
@@ -606,7 +641,7 @@ int eb_rmsd_assign_tc(const float *xyz_soa, const double *traces, int64_t n, int
         tc::k_tc_screen<0><<<grid, tc::THREADS, smem, s>>>(a_img, b_img, traces,
                                                            center_traces, n, k, n_atoms, A_pad,
                                                            kappa, dbg, nullptr, nullptr, nullptr,
-                                                           nullptr, n_seg);
+                                                           nullptr, n_seg, frame_idx);
         EB_LAUNCH_CHECK();
         return EB_OK;
     }
@@ -616,14 +651,14 @@ int eb_rmsd_assign_tc(const float *xyz_soa, const double *traces, int64_t n, int
     tc::k_tc_screen<1><<<grid, tc::THREADS, smem, s>>>(a_img, b_img, traces,
                                                        center_traces, n, k, n_atoms, A_pad, kappa,
                                                        nullptr, seg_count, cand_list, cand_bound,
-                                                       cand_umin, n_seg);
+                                                       cand_umin, n_seg, frame_idx);
     EB_LAUNCH_CHECK();
     long blocks = (n + 31) / 32;
     if (blocks > 8L * sm_count()) blocks = 8L * sm_count();
     tc::k_rescore<<<(int)blocks, 256, 0, s>>>(xyz_soa, traces, n, n_atoms, A_pad, centers_soa,
                                               center_traces, seg_count, cand_list, cand_bound,
-                                              cand_umin, n_seg * tc::EPI_HALVES, out_dist,
-                                              out_assign, cand_count);
+                                              cand_umin, (int)n_lists, out_dist, out_assign,
+                                              cand_count, frame_idx, scatter);
     EB_LAUNCH_CHECK();
     return EB_OK;
 }

@@ -118,6 +118,19 @@ int eb_kcenters_step_rmsd(const float *xyz_soa, const double *traces, int64_t n,
 /* seed: arg-max of the CURRENT dist array -> cand_out (all +inf gives frame 0, which is the
  * reference's first centre, kcenters.py:199,282,326-328); resets *state with
  * n_centers = first_center_id (> 0 when continuing from init_centers, kcenters.py:200-206). */
+/* Triangle-inequality variant of the step (cluster/kcenters.py:287-296,
+ * use_triangle_inequality=True).  center_store (store_capacity x 3*A_pad floats) and
+ * center_store_traces hold the coordinates of the centres chosen so far (slots
+ * [0, n_centers)); cc (store_capacity floats) receives d(new centre, centre j).  k_upper: a host
+ * upper bound of n_centers before the first of the n_steps launches (sizes the small
+ * centre-centre grid).  Results are identical to eb_kcenters_step_rmsd. */
+int eb_kcenters_step_rmsd_tri(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
+                              int64_t frame_offset, const void *cand_in, int n_cand, float *dist,
+                              int32_t *assign, int32_t n_clusters_limit, double dist_cutoff,
+                              eb_kc_state *state, int64_t *center_list, void *partials,
+                              void *cand_out, float *center_store, double *center_store_traces,
+                              float *cc, int64_t store_capacity, int64_t k_upper, int n_steps,
+                              void *stream);
 int eb_kcenters_seed_rmsd(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
                           int64_t frame_offset, const float *dist, int32_t first_center_id,
                           eb_kc_state *state, void *partials, void *cand_out, void *stream);
@@ -163,15 +176,19 @@ int eb_feat_one_to_all(const void *X, int64_t n, int64_t n_features, int dtype, 
  * bound does not exceed the frame's best upper bound survive (error model: |d msd| <=
  * kappa * sqrt(Ga*Gb) / n_atoms) and are re-scored exactly in float64 with the reference's
  * strict-'<' centre order.  cand_count[f] receives the number of centres re-scored for frame f,
- * or -1 if a candidate list overflowed (64 per centre segment); those frames are NOT written and
- * must be sent through eb_rmsd_assign (frame_idx subset).  scratch: eb_tc_scratch_bytes(n, n_atoms, k).  Requires
+ * or -1 if a candidate list overflowed (32 per list); those frames are NOT written and must be
+ * sent through eb_rmsd_assign (frame_idx subset).  frame_idx (optional, int64[n]) restricts the
+ * pass to frames frame_idx[0..n) of xyz_soa (PAM's X[dst_up_assig_this], kmedoids.py:666-667):
+ * cand_count is indexed by position, results go to position i or, with `scatter`, to
+ * frame_idx[i].  scratch: eb_tc_scratch_bytes(n, n_atoms, k).  Requires
  * eb_rmsd_apad(n_atoms) % 16 == 0.  mode 0 is a debugging aid: dbg (n*k*9 floats) receives the
  * approximate inner-product matrices and nothing else is written. */
 size_t eb_tc_scratch_bytes(int64_t n, int n_atoms, int32_t k);
 int eb_rmsd_assign_tc(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
                       const float *centers_soa, const double *center_traces, int32_t k,
-                      double kappa, float *out_dist, int32_t *out_assign, int32_t *cand_count,
-                      void *scratch, float *dbg, int mode, void *stream);
+                      double kappa, const int64_t *frame_idx, int scatter, float *out_dist,
+                      int32_t *out_assign, int32_t *cand_count, void *scratch, float *dbg,
+                      int mode, void *stream);
 
 /* ---- K3 for feature vectors (same contract as eb_rmsd_assign) */
 int eb_feat_assign(const void *X, int64_t n, int64_t n_features, int dtype, int metric,

@@ -15,7 +15,8 @@ def run(n, k, A):
     scratch = torch.zeros(int(L.eb_tc_scratch_bytes(n, A, k)), dtype=torch.uint8, device="cuda")
     dbg = torch.zeros((n, k, 9), dtype=torch.float32, device="cuda")
     _lib.call("eb_rmsd_assign_tc", ptr(data.xyz), ptr(data.traces), n, A, ptr(cen.xyz),
-              ptr(cen.traces), k, 0.0, None, None, None, ptr(scratch), ptr(dbg), 0, stream_ptr())
+              ptr(cen.traces), k, 0.0, None, 0, None, None, None, ptr(scratch), ptr(dbg), 0,
+              stream_ptr())
     torch.cuda.synchronize()
     xs = data.xyz.cpu().numpy().astype(np.float64)      # (n,3,Ap)
     cs = cen.xyz.cpu().numpy().astype(np.float64)       # (k,3,Ap)
@@ -62,7 +63,8 @@ def calibrate(n, k, A, seed):
     scratch = torch.zeros(int(L.eb_tc_scratch_bytes(n, A, k)), dtype=torch.uint8, device="cuda")
     dbg = torch.zeros((n, k, 9), dtype=torch.float32, device="cuda")
     _lib.call("eb_rmsd_assign_tc", ptr(data.xyz), ptr(data.traces), n, A, ptr(cen.xyz),
-              ptr(cen.traces), k, 0.0, None, None, None, ptr(scratch), ptr(dbg), 0, stream_ptr())
+              ptr(cen.traces), k, 0.0, None, 0, None, None, None, ptr(scratch), ptr(dbg), 0,
+              stream_ptr())
     torch.cuda.synchronize()
     xs = data.xyz.cpu().numpy().astype(np.float64)
     cs = cen.xyz.cpu().numpy().astype(np.float64)

@@ -29,6 +29,10 @@ def main():
         ok &= np.array_equal(shard.assignments, serial.assignments[bounds[rank]:bounds[rank + 1]])
         ok &= np.array_equal(shard.distances, serial.distances[bounds[rank]:bounds[rank + 1]])
         ok &= len(shard.centers) == len(serial.centers)
+        tri = kcenters.kcenters(mine, "rmsd", mpi_mode=True, use_triangle_inequality=True, **kw)
+        ok &= [tuple(c) for c in tri.center_indices] == [tuple(c) for c in shard.center_indices]
+        ok &= np.array_equal(tri.assignments, shard.assignments)
+        ok &= np.array_equal(tri.distances, shard.distances)
         for a, b in zip(shard.centers, serial.centers):
             ok &= np.array_equal(np.asarray(a).reshape(-1), np.asarray(b).reshape(-1))
     # features, euclidean, exact

@@ -211,3 +211,43 @@ def test_kcenters_full_size_properties(cuda):
     # (checked through the final distances: nobody is farther than the last radius)
     last_radius = util.RMSD(X[c[:-1]], X[c[-1]]).min()
     assert r.distances.max() <= last_radius + 1e-6
+
+
+def test_triangle_inequality_equals_plain(cuda, frame0_xyz):
+    """enspara/test/test_cluster.py:710-770: use_triangle_inequality must not change anything
+    (centres, assignments, distances) -- here it prunes HBM reads instead of Python work."""
+    from enspara_b200 import synth
+    from enspara_b200.cluster import kcenters
+    from enspara_b200.cluster._engine import KCentersEngine
+    from oracle import distances as od
+    cases = [(od.Trajectory(frame0_xyz), dict(dist_cutoff=0.1)),
+             (od.Trajectory(frame0_xyz), dict(n_clusters=40)),
+             (synth.trajectory(20000, 50, seed=4), dict(n_clusters=300)),
+             (synth.trajectory(3001, 264, seed=5), dict(dist_cutoff=0.45, n_clusters=500)),
+             (synth.trajectory(33, 10, seed=6), dict(n_clusters=33))]
+    for X, kw in cases:
+        a = kcenters.kcenters(X, "rmsd", **kw)
+        b, eng = kcenters.kcenters(X, "rmsd", use_triangle_inequality=True, _return_engine=True,
+                                   **kw)
+        assert eng.triangle
+        assert [int(c) for c in a.center_indices] == [int(c) for c in b.center_indices]
+        assert np.array_equal(a.assignments, b.assignments)
+        assert np.array_equal(a.distances, b.distances)
+
+
+def test_triangle_inequality_warm_start(cuda):
+    """init_centers + triangle pruning: the supplied centres seed the centre store."""
+    from enspara_b200 import synth
+    from enspara_b200.cluster import kcenters
+    X = synth.trajectory(5000, 40, seed=8)
+    first = kcenters.kcenters(X, "rmsd", n_clusters=20)
+    init = [X[int(i)] for i in first.center_indices]
+    a = kcenters.kcenters(X, "rmsd", n_clusters=60, init_centers=init)
+    b = kcenters.kcenters(X, "rmsd", n_clusters=60, init_centers=init,
+                          use_triangle_inequality=True)
+    assert [int(c) for c in a.center_indices] == [int(c) for c in b.center_indices]
+    assert np.array_equal(a.assignments, b.assignments)
+    assert np.array_equal(a.distances, b.distances)
+    # and a warm start continues exactly where the cold run would have gone
+    cold = kcenters.kcenters(X, "rmsd", n_clusters=60)
+    assert [int(c) for c in cold.center_indices][20:] == [int(c) for c in b.center_indices][20:]

@@ -48,15 +48,83 @@ def test_tc_assign_matches_oracle(cuda):
 
 
 def test_tc_overflow_falls_back_to_exact(cuda):
-    """Many identical centres -> every frame has > 128 survivors -> exact fallback, same result."""
+    """Many identical centres -> a candidate list (32 entries; a list covers 48 centres here)
+    overflows for every frame -> exact fallback, same result."""
     from enspara_b200 import synth
     from enspara_b200.cluster import _ops, util
     from enspara_b200.device import DeviceTrajectory
-    data = DeviceTrajectory.from_host(synth.trajectory(600, 64, seed=2))
-    cen = data.gather(np.array([5] * 150 + [17] * 150, dtype=np.int64))
+    data = DeviceTrajectory.from_host(synth.trajectory(9600, 64, seed=2))
+    cen = data.gather(np.array([5] * 192 + [17] * 192, dtype=np.int64))
     d0, a0 = _ops.assign_device(util.RMSD, data, cen)
     stats = {}
     d1, a1 = _ops.assign_device_tc(util.RMSD, data, cen, stats=stats)
     assert stats["overflow_frames"] > 0
     assert cuda.equal(a0, a1) and cuda.equal(d0, d1)
-    assert set(np.unique(a1.cpu().numpy())) <= {0, 150}     # lowest index among duplicates
+    assert set(np.unique(a1.cpu().numpy())) <= {0, 192}     # lowest index among duplicates
+
+
+@pytest.mark.parametrize("n,A,k,m", [(6000, 500, 200, 700), (3000, 48, 1000, 37),
+                                     (2000, 240, 64, 2000), (5000, 96, 333, 129)])
+def test_tc_subset_scatter_equals_exact(cuda, n, A, k, m):
+    """Frame subsets (PAM's X[dst_up_assig_this], kmedoids.py:666-667): the screen restricted to
+    `frame_idx` with scattered outputs equals the exact kernel on the same subset, and leaves
+    every other frame's entry untouched."""
+    torch = cuda
+    from enspara_b200 import synth
+    from enspara_b200.cluster import _ops, util
+    from enspara_b200.device import DeviceTrajectory
+    data = DeviceTrajectory.from_host(synth.trajectory(n, A, seed=n + k))
+    cen = data.gather(np.linspace(0, n - 1, k).astype(np.int64))
+    rs = np.random.RandomState(m)
+    idx = torch.as_tensor(np.sort(rs.choice(n, m, replace=False)), device="cuda")
+    buf = torch.cat([idx, torch.zeros(50, dtype=torch.int64, device="cuda")])  # longer buffer
+    d0 = torch.full((n,), -7.0, device="cuda")
+    a0 = torch.full((n,), -7, dtype=torch.int32, device="cuda")
+    d1, a1 = d0.clone(), a0.clone()
+    _ops.assign_device(util.RMSD, data, cen, frame_idx=buf, n_idx=m, out_dist=d0, out_assign=a0,
+                       scatter=True)
+    ws = {}
+    for _ in range(2):       # second call reuses the workspace
+        _ops.assign_device_tc(util.RMSD, data, cen, frame_idx=buf, n_idx=m, out_dist=d1,
+                              out_assign=a1, scatter=True, workspace=ws)
+    assert torch.equal(a0, a1) and torch.equal(d0, d1)
+    untouched = torch.ones(n, dtype=torch.bool, device="cuda")
+    untouched[idx] = False
+    assert bool((d1[untouched] == -7.0).all()) and bool((a1[idx] >= 0).all())
+    # compact (non-scatter) form
+    d2, a2 = _ops.assign_device_tc(util.RMSD, data, cen, frame_idx=idx)
+    assert torch.equal(d2, d1[idx]) and torch.equal(a2, a1[idx])
+
+
+def test_pam_sweep_uses_tc_and_matches_exact_path(cuda):
+    """A PAM sweep with enough medoids for the tensor-core subset path gives exactly what the
+    exact-kernel sweep gives (medoids, assignments, distances) and what the oracle gives."""
+    from enspara_b200 import synth
+    from enspara_b200.cluster import kcenters, util
+    from enspara_b200.cluster._pam import PamEngine
+    from enspara_b200.cluster.kcenters import _SingleComm
+    from enspara_b200.device import DeviceTrajectory
+    from oracle import cluster as oc
+    from oracle import distances as od
+    X = synth.trajectory(4000, 32, seed=21)
+    data = DeviceTrajectory.from_host(X)
+    r = kcenters.kcenters(data, "rmsd", n_clusters=80)
+    ctr = [int(c) for c in r.center_indices]
+    out = []
+    for use_tc in (True, False):
+        pam = PamEngine(data, util.RMSD, _SingleComm(), r.distances, r.assignments, ctr)
+        assert pam.use_tc
+        pam.use_tc = use_tc
+        pam.TC_MIN_PAIRS = 1
+        acc = pam.sweep(random_state=3)
+        a, d = pam.results_host()
+        out.append((list(pam.medoid_global), a, d, acc))
+    assert out[0][0] == out[1][0] and out[0][3] == out[1][3]
+    assert_array_equal(out[0][1], out[1][1])
+    assert_array_equal(out[0][2], out[1][2])
+    T = od.Trajectory(X)
+    ind, d, a, _ = oc.pam_update(T, od.rmsd, list(ctr), r.assignments.copy(),
+                                 r.distances.copy(), random_state=3)
+    assert [int(i) for i in ind] == out[0][0]
+    assert_array_equal(a, out[0][1])
+    assert_allclose(d, out[0][2], rtol=1e-5, atol=1e-6)
