@@ -141,8 +141,7 @@ TC_KAPPA_PER_ATOM = 8.0 * 2.0 ** -24
 
 
 def tc_applicable(metric, data, k):
-    return (metric.is_rmsd and k >= TC_MIN_CENTERS and data.a_pad % 16 == 0
-            and len(data) >= 128)
+    return metric.is_rmsd and k >= TC_MIN_CENTERS and len(data) >= 1
 
 
 def assign_device_tc(metric, data, centers, k=None, stats=None, frame_idx=None, n_idx=None,

@@ -27,8 +27,10 @@ from ._engine import ShardInfo
 
 
 class PamEngine:
-    #: (frame, medoid) pairs below which the exact kernel is used for the ambiguous subset
-    TC_MIN_PAIRS = 1 << 15
+    #: (frame, medoid) pairs below which the exact kernel is used for the ambiguous subset.
+    #: The exact kernel walks all medoids serially per frame (3 us per medoid), so with >= 64
+    #: medoids even a one-frame subset is faster through the screen (~0.1 ms fixed cost).
+    TC_MIN_PAIRS = 0
 
     def __init__(self, data, metric, comm, distances, assignments, medoid_global_inds):
         self.data = data

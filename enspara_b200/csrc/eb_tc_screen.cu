@@ -20,6 +20,8 @@
 //
 // Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2-5
 // epilogue (TMEM lane quarter = warp_id % 4).
+#include <stdlib.h>
+
 #include "eb_rmsd.cuh"
 #include "eb_tma.cuh"
 
@@ -36,7 +38,8 @@ constexpr int B_TILE = BN * BK * 4;      // 6144
 constexpr int STAGE_BYTES = 6 * A_TILE + 2 * B_TILE;  // {hi,lo} x 3 coords of A, {hi,lo} of B
 constexpr int TMEM_COLS = 512;           // 3 accumulators x 144 columns = 432 -> power of two
 constexpr int THREADS = 64 + 128 * 2;  // producer, MMA, 8 epilogue warps
-constexpr int MAX_CAND = 32;   // survivors kept per candidate list
+constexpr int CAND_BUDGET = 256;  // candidate entries per frame, shared out over its lists
+constexpr int MIN_CAND = 8;       // ... but never fewer than this per list
 constexpr int DEF_SEG = 4;     // centre segments: CTAs sharing a frame tile hit it in L2
 constexpr int MAX_SEG = 32;    // small frame subsets (PAM) are spread over more segments
 constexpr int EPI_HALVES = 2;  // two epilogue warps per TMEM lane quarter, NC/2 centres each
@@ -58,8 +61,9 @@ __global__ void __launch_bounds__(256)
 k_pack_tf32(const float *__restrict__ x, long rows_total, int A_pad, int RT, int S, long n_tiles,
             const int64_t *__restrict__ row_idx, unsigned char *__restrict__ img)
 {
-    const int Q = A_pad >> 2;  // float4 per row
-    const int KB = A_pad / BK;
+    const int Qs = A_pad >> 2;               // float4 per source row
+    const int KB = (A_pad + BK - 1) / BK;    // k-blocks of the image (zero-padded to 16 atoms)
+    const int Q = KB * (BK / 4);             // float4 per image row
     const long total = n_tiles * RT * S * (long)Q;
     const size_t tile_bytes = (size_t)RT * 64;
     for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -71,7 +75,7 @@ k_pack_tf32(const float *__restrict__ x, long rows_total, int A_pad, int RT, int
         const long T = tr / RT;
         const int r = (int)(tr - T * RT);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (rr < rows_total) {
+        if (rr < rows_total && q < Qs) {
             const long src = row_idx ? (long)__ldg(row_idx + tr) * S + sidx : rr;
             v = __ldg(reinterpret_cast<const float4 *>(x + (size_t)src * A_pad) + q);
         }
@@ -201,14 +205,15 @@ __global__ void __launch_bounds__(THREADS, 1)
 k_tc_screen(const unsigned char *__restrict__ a_img, const unsigned char *__restrict__ b_img,
             const double *__restrict__ traces, const double *__restrict__ ctraces, long n, int k,
             int n_atoms, int A_pad, double kappa, float *dbg, int *cand_count, int *cand_list,
-            float *cand_bound, float *cand_umin, int n_seg, const int64_t *__restrict__ frame_idx)
+            float *cand_bound, float *cand_umin, int n_seg, const int64_t *__restrict__ frame_idx,
+            int MAX_CAND)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *tiles = smem_raw;
     Smem *sm = reinterpret_cast<Smem *>(tiles + (size_t)STAGES * STAGE_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int KB = A_pad / BK;
+    const int KB = (A_pad + BK - 1) / BK;
     const int n_ct = (k + NC - 1) / NC;
     const long n_ft = (n + BM - 1) / BM;
     // work item = (frame tile, centre segment); consecutive CTAs take the segments of the SAME
@@ -458,87 +463,138 @@ k_tc_screen(const unsigned char *__restrict__ a_img, const unsigned char *__rest
 }
 
 // ---- exact re-scoring of the surviving (frame, centre) pairs ---------------------------------
-// A group of 8 lanes owns one frame and walks its candidate list in ascending centre order with
-// the strict '<' of cluster/util.py:201; centres are read from global memory (few pairs).
-__global__ void __launch_bounds__(256)
+// A group of 8 lanes owns one frame: it merges the frame's candidate lists (global upper bound
+// U = min over lists; survivors = entries whose lower bound does not exceed U) into one compact
+// list in shared memory, stages the frame's coordinates in shared memory once, and then scores
+// two centres per pass with the exact float64 arithmetic of the reference path (float x float
+// products are exact in double; QCP in double; float32 result).  Ties: lowest centre index, which
+// is what strict '<' in centre order gives (cluster/util.py:201).  Centres come from L2.
+constexpr int RS_GROUPS = 16;            // frames per block
+constexpr int RS_THREADS = RS_GROUPS * 8;
+
+template <bool STAGE>
+__global__ void __launch_bounds__(RS_THREADS)
 k_rescore(const float *__restrict__ xyz, const double *__restrict__ traces, long n, int n_atoms,
           int A_pad, const float *__restrict__ centers, const double *__restrict__ ctraces,
           const int *__restrict__ cand_count, const int *__restrict__ cand_list,
           const float *__restrict__ cand_bound, const float *__restrict__ cand_umin, int n_seg,
           float *out_dist, int *out_assign, int *frame_flag,
-          const int64_t *__restrict__ frame_idx, int scatter)
+          const int64_t *__restrict__ frame_idx, int scatter, int MAX_CAND)
 {
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    const int list_cap = n_seg * MAX_CAND;
+    int *cl_all = reinterpret_cast<int *>(rs_smem);                       // [RS_GROUPS][list_cap]
+    float *fr_all = reinterpret_cast<float *>(rs_smem + align16(sizeof(int) * RS_GROUPS * list_cap));
     const int lane = threadIdx.x & 31, g = lane >> 3, l8 = lane & 7;
+    const int grp = threadIdx.x >> 3;                                    // group within the block
     const int A4 = A_pad >> 2;
     const size_t stride = 3 * (size_t)A_pad;
-    const long groups = (long)gridDim.x * (blockDim.x >> 3);
-    for (long fb = ((long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4; fb < n;
-         fb += groups) {
-        const long f = fb + g;
+    int *cl = cl_all + (size_t)grp * list_cap;
+    float *fr = fr_all + (size_t)grp * stride;
+    const long groups = (long)gridDim.x * RS_GROUPS;
+    const long n_round = (n + groups - 1) / groups * groups;   // every warp runs the same trips
+    for (long fb = (long)blockIdx.x * RS_GROUPS + grp; fb < n_round; fb += groups) {
+        const long f = fb;
         const bool valid = f < n;
-        // merge the segments: global upper bound, overflow if any segment overflowed
+        // merge the lists: global upper bound, overflow if any list overflowed
         float U = INFINITY;
-        bool overflow = false;
-        int total = 0;
+        int ovf = 0;
         if (valid) {
-            for (int sgm = 0; sgm < n_seg; ++sgm) {
+            for (int sgm = l8; sgm < n_seg; sgm += 8) {
                 U = fminf(U, cand_umin[(size_t)f * n_seg + sgm]);
-                const int cnt = cand_count[(size_t)f * n_seg + sgm];
-                overflow |= cnt < 0;
-                total += max(cnt, 0);
+                ovf |= cand_count[(size_t)f * n_seg + sgm] < 0;
             }
         }
-        float best_d = INFINITY;
-        int best_c = 0, evaluated = 0;
+#pragma unroll
+        for (int msk = 1; msk < 8; msk <<= 1) {
+            U = fminf(U, __shfl_xor_sync(0xffffffffu, U, msk));
+            ovf |= __shfl_xor_sync(0xffffffffu, ovf, msk);
+        }
+        const bool overflow = ovf != 0;
         const long src = valid ? (frame_idx ? (long)frame_idx[f] : f) : 0;  // row of xyz / traces
         const float4 *px = reinterpret_cast<const float4 *>(xyz + (size_t)src * stride);
+        if (STAGE && valid && !overflow) {
+            float4 *dst = reinterpret_cast<float4 *>(fr);
+            for (int t = l8; t < 3 * A4; t += 8) dst[t] = __ldg(px + t);
+        }
+        // compact the survivors of all lists into cl[0 .. cnt_g)
+        int cnt_g = 0;
         for (int sgm = 0; sgm < n_seg; ++sgm) {
             const int cnt = (valid && !overflow) ? cand_count[(size_t)f * n_seg + sgm] : 0;
-            int cnt_max = cnt;
-            cnt_max = max(cnt_max, __shfl_xor_sync(0xffffffffu, cnt_max, 8));
-            cnt_max = max(cnt_max, __shfl_xor_sync(0xffffffffu, cnt_max, 16));
+            int cmax = cnt;
+            cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, 8));
+            cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, 16));
             const size_t slot = ((size_t)(valid ? f : 0) * n_seg + sgm) * MAX_CAND;
-            for (int s = 0; s < cnt_max; ++s) {
-                const bool act = s < cnt && cand_bound[slot + s] <= U;
-                const int c = act ? cand_list[slot + s] : 0;
-                const float4 *pc = reinterpret_cast<const float4 *>(centers + (size_t)c * stride);
-                double m[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-                if (act) {
-                    for (int j = l8; j < A4; j += 8) {
-                        const float4 x = __ldg(px + j), y = __ldg(px + A4 + j),
-                                     z = __ldg(px + 2 * A4 + j);
-                        const float4 cx = __ldg(pc + j), cy = __ldg(pc + A4 + j),
-                                     cz = __ldg(pc + 2 * A4 + j);
-                        acc_atom(m, x.x, y.x, z.x, (double)cx.x, (double)cy.x, (double)cz.x);
-                        acc_atom(m, x.y, y.y, z.y, (double)cx.y, (double)cy.y, (double)cz.y);
-                        acc_atom(m, x.z, y.z, z.z, (double)cx.z, (double)cy.z, (double)cz.z);
-                        acc_atom(m, x.w, y.w, z.w, (double)cx.w, (double)cy.w, (double)cz.w);
-                    }
+            for (int s0 = 0; s0 < cmax; s0 += 8) {
+                const int sidx = s0 + l8;
+                const bool act = sidx < cnt && cand_bound[slot + sidx] <= U;
+                const int c = act ? cand_list[slot + sidx] : 0;
+                const unsigned b = __ballot_sync(0xffffffffu, act);
+                const unsigned gb = (b >> (8 * g)) & 0xffu;
+                if (act) cl[cnt_g + __popc(gb & ((1u << l8) - 1u))] = c;
+                cnt_g += __popc(gb);
+            }
+        }
+        __syncwarp();
+        int tmax = cnt_g;
+        tmax = max(tmax, __shfl_xor_sync(0xffffffffu, tmax, 8));
+        tmax = max(tmax, __shfl_xor_sync(0xffffffffu, tmax, 16));
+        float best_d = INFINITY;
+        int best_c = 0;
+        const double Ga = valid ? traces[src] : 0.0;
+        const float4 *sx = STAGE ? reinterpret_cast<const float4 *>(fr) : px;
+        for (int i0 = 0; i0 < tmax; i0 += 2) {
+            const bool act0 = i0 < cnt_g, act1 = i0 + 1 < cnt_g;
+            const int c0 = act0 ? cl[i0] : 0, c1 = act1 ? cl[i0 + 1] : c0;
+            const float4 *p0 = reinterpret_cast<const float4 *>(centers + (size_t)c0 * stride);
+            const float4 *p1 = reinterpret_cast<const float4 *>(centers + (size_t)c1 * stride);
+            double m0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, m1[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            if (act0) {
+#pragma unroll 2
+                for (int j = l8; j < A4; j += 8) {
+                    const float4 x = sx[j], y = sx[A4 + j], z = sx[2 * A4 + j];
+                    const float4 ax = __ldg(p0 + j), ay = __ldg(p0 + A4 + j),
+                                 az = __ldg(p0 + 2 * A4 + j);
+                    const float4 bx = __ldg(p1 + j), by = __ldg(p1 + A4 + j),
+                                 bz = __ldg(p1 + 2 * A4 + j);
+                    acc_atom(m0, x.x, y.x, z.x, (double)ax.x, (double)ay.x, (double)az.x);
+                    acc_atom(m0, x.y, y.y, z.y, (double)ax.y, (double)ay.y, (double)az.y);
+                    acc_atom(m0, x.z, y.z, z.z, (double)ax.z, (double)ay.z, (double)az.z);
+                    acc_atom(m0, x.w, y.w, z.w, (double)ax.w, (double)ay.w, (double)az.w);
+                    acc_atom(m1, x.x, y.x, z.x, (double)bx.x, (double)by.x, (double)bz.x);
+                    acc_atom(m1, x.y, y.y, z.y, (double)bx.y, (double)by.y, (double)bz.y);
+                    acc_atom(m1, x.z, y.z, z.z, (double)bx.z, (double)by.z, (double)bz.z);
+                    acc_atom(m1, x.w, y.w, z.w, (double)bx.w, (double)by.w, (double)bz.w);
                 }
-                group8_reduce(m);
-                if (act) {
-                    const float d = rmsd_from_msd(qcp_msd(m, traces[src], ctraces[c], n_atoms));
-                    ++evaluated;
-                    // lists are not globally ordered by centre: lowest centre index on exact
-                    // ties, which is what strict '<' in centre order gives (util.py:201)
-                    if (d < best_d || (d == best_d && c < best_c)) {
-                        best_d = d;
-                        best_c = c;
-                    }
+            }
+            group8_reduce(m0);
+            group8_reduce(m1);
+            if (act0) {
+                const float d = rmsd_from_msd(qcp_msd(m0, Ga, ctraces[c0], n_atoms));
+                if (d < best_d || (d == best_d && c0 < best_c)) {
+                    best_d = d;
+                    best_c = c0;
+                }
+            }
+            if (act1) {
+                const float d = rmsd_from_msd(qcp_msd(m1, Ga, ctraces[c1], n_atoms));
+                if (d < best_d || (d == best_d && c1 < best_c)) {
+                    best_d = d;
+                    best_c = c1;
                 }
             }
         }
         if (valid && l8 == 0) {
-            if (overflow || evaluated == 0) {
+            if (overflow || cnt_g == 0) {
                 frame_flag[f] = -1;  // the host sends this frame through the exact kernel
             } else {
-                frame_flag[f] = evaluated;
+                frame_flag[f] = cnt_g;
                 const long o = scatter ? src : f;
                 out_dist[o] = best_d;
                 out_assign[o] = best_c;
             }
         }
-        (void)total;
+        __syncwarp();
     }
 }
 
@@ -550,9 +606,25 @@ using namespace eb;
 // Centre segments per frame tile: the default keeps consecutive CTAs on one frame tile (its A
 // operand is then served by L2); a small frame subset (PAM's ambiguous frames) is cut into more
 // segments so that every SM gets a work item.
+static int tc_def_seg()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("EB_TC_SEG");   // developer A/B switch
+        v = e ? atoi(e) : tc::DEF_SEG;
+        if (v < 1 || v > tc::MAX_SEG) v = tc::DEF_SEG;
+    }
+    return v;
+}
+static int tc_max_cand(int n_lists)
+{
+    const int c = tc::CAND_BUDGET / n_lists;
+    return c < tc::MIN_CAND ? tc::MIN_CAND : c;
+}
 static int tc_pick_nseg(long n_ft, int n_ct)
 {
-    int n_seg = n_ct < tc::DEF_SEG ? n_ct : tc::DEF_SEG;
+    const int def_seg = tc_def_seg();
+    int n_seg = n_ct < def_seg ? n_ct : def_seg;
     const long want = 2L * sm_count();
     if (n_ft * n_seg < want) {
         long s2 = (want + n_ft - 1) / n_ft;
@@ -560,14 +632,18 @@ static int tc_pick_nseg(long n_ft, int n_ct)
         if (s2 > n_ct) s2 = n_ct;
         if (s2 > n_seg) n_seg = (int)s2;
     }
-    return n_seg < 1 ? 1 : n_seg;
+    if (n_seg < 1) n_seg = 1;
+    // drop segments that would be empty: ceil(n_ct / ceil(n_ct / n_seg))
+    const int per = (n_ct + n_seg - 1) / n_seg;
+    return (n_ct + per - 1) / per;
 }
 
 extern "C" {
 
 size_t eb_tc_scratch_bytes(int64_t n, int n_atoms, int32_t k)
 {
-    const size_t row = sizeof(float) * 3 * (size_t)rmsd_apad(n_atoms);
+    const size_t row = sizeof(float) * 3 *
+                       (size_t)((rmsd_apad(n_atoms) + tc::BK - 1) / tc::BK * tc::BK);
     const long n_ft = (n + tc::BM - 1) / tc::BM;
     const int n_ct = (k + tc::NC - 1) / tc::NC;
     const size_t n_lists = (size_t)tc_pick_nseg(n_ft < 1 ? 1 : n_ft, n_ct < 1 ? 1 : n_ct) *
@@ -575,7 +651,8 @@ size_t eb_tc_scratch_bytes(int64_t n, int n_atoms, int32_t k)
     // split copies of frames and centres + candidate lists
     return 2 * row * (size_t)(n + tc::BM) + 2 * row * (size_t)(k + tc::NC) +
            (size_t)n * n_lists *
-               (sizeof(int) + sizeof(float) + tc::MAX_CAND * (sizeof(int) + sizeof(float))) +
+               (sizeof(int) + sizeof(float) +
+                tc_max_cand((int)n_lists) * (sizeof(int) + sizeof(float))) +
            4096;
 }
 
@@ -599,8 +676,8 @@ int eb_rmsd_assign_tc(const float *xyz_soa, const double *traces, int64_t n, int
     EB_CHECK_ARG(n < (1L << 31) / 3, "rmsd_assign_tc: too many frames for one pass");
     cudaStream_t s = (cudaStream_t)stream;
     const int A_pad = rmsd_apad(n_atoms);
-    EB_CHECK_ARG(A_pad % tc::BK == 0, "rmsd_assign_tc: padded atom count must be a multiple of 16");
-    const size_t row = 3 * (size_t)A_pad;  // floats per frame
+    const int A_img = (A_pad + tc::BK - 1) / tc::BK * tc::BK;   // image rows padded to 16 atoms
+    const size_t row = 3 * (size_t)A_img;  // floats per frame in the packed images
     // packed operand images (tile-padded): frames then centres
     const size_t a_rows = (size_t)((n + tc::BM - 1) / tc::BM) * tc::BM;   // frames, padded
     const size_t c_rows = (size_t)((k + tc::NC - 1) / tc::NC) * tc::NC;   // centres, padded
@@ -612,19 +689,20 @@ int eb_rmsd_assign_tc(const float *xyz_soa, const double *traces, int64_t n, int
     const int n_seg = tc_pick_nseg(n_ft, n_ct_total);
     const size_t n_lists = (size_t)n_seg * tc::EPI_HALVES;
     int *cand_list = (int *)lists;
-    float *cand_bound = (float *)(cand_list + (size_t)n * n_lists * tc::MAX_CAND);
-    float *cand_umin = cand_bound + (size_t)n * n_lists * tc::MAX_CAND;
+    const int max_cand = tc_max_cand((int)n_lists);
+    float *cand_bound = (float *)(cand_list + (size_t)n * n_lists * max_cand);
+    float *cand_umin = cand_bound + (size_t)n * n_lists * max_cand;
     int *seg_count = (int *)(cand_umin + (size_t)n * n_lists);
 
     {
-        long total = n_ft * tc::BM * 3 * (long)(A_pad / 4);
+        long total = n_ft * tc::BM * 3 * (long)(A_img / 4);
         long blocks = (total + 255) / 256;
         if (blocks > 32L * sm_count()) blocks = 32L * sm_count();
         tc::k_pack_tf32<<<(int)blocks, 256, 0, s>>>(xyz_soa, 3L * n, A_pad, tc::BM, 3, n_ft,
                                                     frame_idx, a_img);
         EB_LAUNCH_CHECK();
         const long b_tiles = n_ct_total;
-        total = b_tiles * tc::BN * (long)(A_pad / 4);
+        total = b_tiles * tc::BN * (long)(A_img / 4);
         blocks = (total + 255) / 256;
         if (blocks > 32L * sm_count()) blocks = 32L * sm_count();
         tc::k_pack_tf32<<<(int)blocks, 256, 0, s>>>(centers_soa, 3L * k, A_pad, tc::BN, 1, b_tiles,
@@ -641,7 +719,7 @@ int eb_rmsd_assign_tc(const float *xyz_soa, const double *traces, int64_t n, int
         tc::k_tc_screen<0><<<grid, tc::THREADS, smem, s>>>(a_img, b_img, traces,
                                                            center_traces, n, k, n_atoms, A_pad,
                                                            kappa, dbg, nullptr, nullptr, nullptr,
-                                                           nullptr, n_seg, frame_idx);
+                                                           nullptr, n_seg, frame_idx, 8);
         EB_LAUNCH_CHECK();
         return EB_OK;
     }
@@ -651,15 +729,30 @@ int eb_rmsd_assign_tc(const float *xyz_soa, const double *traces, int64_t n, int
     tc::k_tc_screen<1><<<grid, tc::THREADS, smem, s>>>(a_img, b_img, traces,
                                                        center_traces, n, k, n_atoms, A_pad, kappa,
                                                        nullptr, seg_count, cand_list, cand_bound,
-                                                       cand_umin, n_seg, frame_idx);
+                                                       cand_umin, n_seg, frame_idx, max_cand);
     EB_LAUNCH_CHECK();
-    long blocks = (n + 31) / 32;
-    if (blocks > 8L * sm_count()) blocks = 8L * sm_count();
-    tc::k_rescore<<<(int)blocks, 256, 0, s>>>(xyz_soa, traces, n, n_atoms, A_pad, centers_soa,
-                                              center_traces, seg_count, cand_list, cand_bound,
-                                              cand_umin, (int)n_lists, out_dist, out_assign,
-                                              cand_count, frame_idx, scatter);
-    EB_LAUNCH_CHECK();
+    {
+        const size_t list_bytes = align16(sizeof(int) * tc::RS_GROUPS * n_lists * max_cand);
+        const size_t stage_bytes = sizeof(float) * tc::RS_GROUPS * 3 * (size_t)A_pad;
+        static int rs_mode = -1;   // developer A/B switch: EB_RS_STAGE=0 forces the unstaged path
+        if (rs_mode < 0) {
+            const char *e = getenv("EB_RS_STAGE");
+            rs_mode = e ? atoi(e) : 1;
+        }
+        const bool stage = rs_mode != 0 && list_bytes + stage_bytes <= 113 * 1024;  // 2 blocks/SM
+        const size_t rs_smem = list_bytes + (stage ? stage_bytes : 0);
+        long blocks = (n + tc::RS_GROUPS - 1) / tc::RS_GROUPS;
+        if (blocks > 8L * sm_count()) blocks = 8L * sm_count();
+        auto kern = stage ? tc::k_rescore<true> : tc::k_rescore<false>;
+        EB_CHECK_ARG(rs_smem <= 227 * 1024, "rmsd_assign_tc: candidate lists too large");
+        EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)rs_smem));
+        kern<<<(int)blocks, tc::RS_THREADS, rs_smem, s>>>(
+            xyz_soa, traces, n, n_atoms, A_pad, centers_soa, center_traces, seg_count, cand_list,
+            cand_bound, cand_umin, (int)n_lists, out_dist, out_assign, cand_count, frame_idx,
+            scatter, max_cand);
+        EB_LAUNCH_CHECK();
+    }
     return EB_OK;
 }
 

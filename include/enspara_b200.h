@@ -180,8 +180,8 @@ int eb_feat_one_to_all(const void *X, int64_t n, int64_t n_features, int dtype, 
  * sent through eb_rmsd_assign (frame_idx subset).  frame_idx (optional, int64[n]) restricts the
  * pass to frames frame_idx[0..n) of xyz_soa (PAM's X[dst_up_assig_this], kmedoids.py:666-667):
  * cand_count is indexed by position, results go to position i or, with `scatter`, to
- * frame_idx[i].  scratch: eb_tc_scratch_bytes(n, n_atoms, k).  Requires
- * eb_rmsd_apad(n_atoms) % 16 == 0.  mode 0 is a debugging aid: dbg (n*k*9 floats) receives the
+ * frame_idx[i].  scratch: eb_tc_scratch_bytes(n, n_atoms, k).  Any n_atoms (the packed
+ * operand images are zero-padded to a multiple of 16 atoms).  mode 0 is a debugging aid: dbg (n*k*9 floats) receives the
  * approximate inner-product matrices and nothing else is written. */
 size_t eb_tc_scratch_bytes(int64_t n, int n_atoms, int32_t k);
 int eb_rmsd_assign_tc(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,

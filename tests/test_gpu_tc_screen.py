@@ -128,3 +128,18 @@ def test_pam_sweep_uses_tc_and_matches_exact_path(cuda):
     assert [int(i) for i in ind] == out[0][0]
     assert_array_equal(a, out[0][1])
     assert_allclose(d, out[0][2], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("n,A,k", [(3000, 22, 100), (2500, 264, 70), (1000, 13, 64), (50, 30, 200)])
+def test_tc_any_atom_count(cuda, n, A, k):
+    """Atom counts whose padded row is not a multiple of 16 (22 -> 24, 264, 13 -> 16): the
+    packed operand images are zero-padded, the result still equals the exact kernel's."""
+    from enspara_b200 import synth
+    from enspara_b200.cluster import _ops, util
+    from enspara_b200.device import DeviceTrajectory
+    data = DeviceTrajectory.from_host(synth.trajectory(n, A, seed=A))
+    cen = data.gather(np.linspace(0, n - 1, k).astype(np.int64))
+    assert _ops.tc_applicable(util.RMSD, data, k)
+    d0, a0 = _ops.assign_device(util.RMSD, data, cen)
+    d1, a1 = _ops.assign_device_tc(util.RMSD, data, cen)
+    assert cuda.equal(a0, a1) and cuda.equal(d0, d1)
