@@ -130,6 +130,28 @@ def measured_peaks():
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the reference's path for this metric, restated (oracle/), bounded sample
 # ---------------------------------------------------------------------------------------------
+def _host_sample(n, n_atoms):
+    """The first n frames of the synthetic trajectory as a host array (generated on the GPU
+    when there is one -- the generators are bit-identical -- because the numpy generator takes
+    minutes at this size; generation is outside every timed region)."""
+    from enspara_b200 import synth
+    try:
+        import torch
+        if torch.cuda.is_available():
+            out = np.empty((n, n_atoms, 3), dtype=np.float32)
+            base = synth.base_conformers(n_atoms, 64, 0)
+            chunk = 125_000
+            for lo in range(0, n, chunk):
+                m = min(chunk, n - lo)
+                out[lo:lo + m] = synth.device_trajectory_aos(m, n_atoms, 0, lo,
+                                                             base=base).cpu().numpy()
+            torch.cuda.empty_cache()
+            return out
+    except Exception:
+        pass
+    return synth.trajectory(n, n_atoms, seed=0)
+
+
 def cpu_kcenters_rate(n_atoms, steps, warmup, target_seconds, sample_frames=None):
     """Times the restated reference k-centers iteration (kcenters.py:282-309 around the
     restated md.rmsd with its per-call copy + centre) on all host threads.  Returns
@@ -137,8 +159,8 @@ def cpu_kcenters_rate(n_atoms, steps, warmup, target_seconds, sample_frames=None
     from enspara_b200 import synth
     from oracle import distances as od
     threads = od.num_threads()
-    n = sample_frames or 100_000
-    X = synth.trajectory(n, n_atoms, seed=0)
+    n = sample_frames or 250_000
+    X = _host_sample(n, n_atoms)
     T = od.Trajectory(X)
     distances = np.full(n, np.inf)
     assignments = np.full(n, -1, dtype=np.int64)
@@ -159,7 +181,7 @@ def cpu_kcenters_rate(n_atoms, steps, warmup, target_seconds, sample_frames=None
         t = time.perf_counter()
         iteration()
         one = time.perf_counter() - t
-        steps = int(min(50, max(3, target_seconds / max(one, 1e-6))))
+        steps = int(min(200, max(3, target_seconds / max(one, 1e-6))))
     t = time.perf_counter()
     for _ in range(steps):
         iteration()
@@ -213,6 +235,8 @@ def run_b200(args):
         raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's version / debug banner goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     comm = mpi.comm if world > 1 else kc_mod._SingleComm()
 
