@@ -78,12 +78,35 @@ k_sumsq_partial(const D *__restrict__ x, long n, double *__restrict__ partials)
     if (threadIdx.x == 0) partials[blockIdx.x] = sh[0];
 }
 
+// one warp, fixed order: lane l adds partials l, l+32, ... in sequence, then a fixed shuffle tree
 __global__ void k_sum_final(const double *__restrict__ partials, int nb, double *out)
 {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double s = 0.0;
-        for (int b = 0; b < nb; ++b) s += partials[b];
-        *out = s;
+    const int lane = threadIdx.x;
+    double s = 0.0;
+    for (int b = lane; b < nb; b += 32) s += partials[b];
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) s += shfl_xor_d(s, m);
+    if (lane == 0) *out = s;
+}
+
+constexpr int kHistMaxBins = 8192;  // 32 KB of shared counters per block
+
+// members per cluster: per-block shared-memory histogram, then one global add per non-empty bin
+__global__ void __launch_bounds__(kPamThreads)
+k_count_members_smem(const int *__restrict__ assign, long n, int k, unsigned long long *counts)
+{
+    extern __shared__ unsigned int hist[];
+    for (int b = threadIdx.x; b < k; b += blockDim.x) hist[b] = 0;
+    __syncthreads();
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int a = assign[i];
+        if (a >= 0 && a < k) atomicAdd(hist + a, 1u);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < k; b += blockDim.x) {
+        const unsigned int c = hist[b];
+        if (c) atomicAdd(counts + b, (unsigned long long)c);
     }
 }
 
@@ -122,16 +145,33 @@ __global__ void k_select_pick(const int *__restrict__ assign, long n, int cid, l
 {
     const int lane = threadIdx.x;
     __shared__ long s_block, s_rem;
-    if (lane == 0) {
+    {
+        // warp-parallel scan of the block counts, 32 at a time (inclusive prefix by shuffles)
         long rem = kth;
-        int b = 0;
-        for (; b < nb; ++b) {
-            const long c = (long)block_counts[b];
-            if (rem < c) break;
-            rem -= c;
+        int found = nb;
+        for (int b0 = 0; b0 < nb && found == nb; b0 += 32) {
+            const int b = b0 + lane;
+            const long c = b < nb ? (long)block_counts[b] : 0;
+            long inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const long up = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += up;
+            }
+            const unsigned hit = __ballot_sync(0xffffffffu, b < nb && rem < inc);
+            if (hit) {
+                const int l = __ffs(hit) - 1;          // first block whose prefix exceeds rem
+                const long before = __shfl_sync(0xffffffffu, inc - c, l);
+                found = b0 + l;
+                rem -= before;
+            } else {
+                rem -= __shfl_sync(0xffffffffu, inc, 31);
+            }
         }
-        s_block = b;
-        s_rem = rem;
+        if (lane == 0) {
+            s_block = found;
+            s_rem = rem;
+        }
     }
     __syncwarp();
     if (s_block >= nb) {
@@ -231,8 +271,15 @@ int eb_count_members(const int32_t *assign, int64_t n, int32_t k, int64_t *count
     cudaStream_t s = (cudaStream_t)stream;
     EB_CUDA(cudaMemsetAsync(counts, 0, sizeof(int64_t) * (size_t)k, s));
     if (n == 0 || k == 0) return EB_OK;
-    k_count_members<<<pam_blocks(n), kPamThreads, 0, s>>>(assign, n, k,
-                                                          (unsigned long long *)counts);
+    if (k <= kHistMaxBins) {
+        int nb = pam_blocks(n);
+        if (nb > 2 * sm_count()) nb = 2 * sm_count();   // few blocks: fewer flushes
+        k_count_members_smem<<<nb, kPamThreads, sizeof(unsigned int) * (size_t)k, s>>>(
+            assign, n, k, (unsigned long long *)counts);
+    } else {
+        k_count_members<<<pam_blocks(n), kPamThreads, 0, s>>>(assign, n, k,
+                                                              (unsigned long long *)counts);
+    }
     EB_LAUNCH_CHECK();
     return EB_OK;
 }
