@@ -234,9 +234,13 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(local_rank)
+    # stdout carries exactly one JSON line: anything libraries print while the run is in
+    # progress (NCCL's version banner is written to fd 1 at communicator creation) is sent to
+    # stderr; the saved descriptor is restored just before the line is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's version / debug banner goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     comm = mpi.comm if world > 1 else kc_mod._SingleComm()
 
@@ -354,6 +358,9 @@ def run_b200(args):
         except Exception as exc:  # the oracle is optional for the GPU arm
             cpu = {"error": repr(exc)}
 
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,

@@ -58,7 +58,7 @@ class PamEngine:
         self.counts = torch.zeros(max(self.k, 1), dtype=torch.int64, device=dev)
         self.medoid_global = [int(g) for g in medoid_global_inds]
         self.medoids = self._fetch_frames(self.medoid_global)
-        self.prop = self._fetch_frames([])   # 1-frame scratch, filled per proposal
+        self.prop, self.prop_buf, self.prop_idx = self._proposal_slot()
         self.saved = self._fetch_frames([])  # 1-frame scratch: the medoid a proposal displaces
         self.cost_num = self._sumsq(self.dist)
         self.n_global = self.shard.n_global
@@ -81,6 +81,25 @@ class PamEngine:
             return DeviceTrajectory.empty(m, self.data.n_atoms, self.data.top)
         return DeviceFeatures(torch.zeros((m, self.data.n_features), dtype=self.data.X.dtype,
                                           device=self.dev))
+
+    def _proposal_slot(self):
+        """One flat buffer [frame payload | trace (f64) | global index (i64)] so that a sharded
+        proposal travels in ONE broadcast; returns (1-frame container viewing the payload,
+        the flat buffer, the int64 view of the index)."""
+        if self.is_rmsd:
+            a_pad = self.data.a_pad
+            nf = 3 * a_pad
+            buf = torch.zeros(nf + 4, dtype=torch.float32, device=self.dev)
+            xyz = buf[:nf].view(1, 3, a_pad)
+            traces = buf[nf:nf + 2].view(torch.float64)
+            idx = buf[nf + 2:nf + 4].view(torch.int64)
+            return DeviceTrajectory(xyz, traces, self.data.n_atoms, self.data.top), buf, idx
+        row_bytes = self.data.n_features * self.data.X.element_size()
+        pad = (row_bytes + 7) // 8 * 8
+        buf = torch.zeros(pad + 8, dtype=torch.uint8, device=self.dev)
+        X = buf[:row_bytes].view(self.data.X.dtype).view(1, self.data.n_features)
+        idx = buf[pad:pad + 8].view(torch.int64)
+        return DeviceFeatures(X), buf, idx
 
     def _fetch_frames(self, global_inds):
         """Dense device copy of the frames with these GLOBAL indices on every rank."""
@@ -127,8 +146,12 @@ class PamEngine:
         are cached on the host between acceptances (one histogram launch + one small D2H)."""
         _lib.call("eb_count_members", ptr(self.assign), self.n, self.k, ptr(self.counts),
                   stream_ptr())
-        local = self.counts[:self.k].cpu().numpy().astype(np.int64)
-        self.counts_by_rank = np.stack(self.comm.all_gather_object(local))  # (ranks, k)
+        if self.shard.size > 1:
+            allc = torch.empty(self.shard.size * self.k, dtype=torch.int64, device=self.dev)
+            self.comm.all_gather_into(allc, self.counts[:self.k].contiguous())
+            self.counts_by_rank = allc.view(self.shard.size, self.k).cpu().numpy()
+        else:
+            self.counts_by_rank = self.counts[:self.k].cpu().numpy().astype(np.int64)[None]
 
     def _member_counts(self, cid):
         return self.counts_by_rank[:, cid]
@@ -141,7 +164,9 @@ class PamEngine:
             dst.X[j].copy_(src.X[i])
 
     def _load_proposal(self, owner, local_idx_dev=None, local_idx=None):
-        """Make self.prop (1 frame) hold the proposed centre on every rank."""
+        """Make self.prop (1 frame) and self.prop_idx (its GLOBAL index) valid on every rank:
+        the owner gathers the frame, one broadcast of the flat buffer does the rest
+        (the reference: bcast of the index + Bcast of the frame, kmedoids.py:500-508)."""
         sh = self.shard
         if sh.rank == owner:
             idx = local_idx_dev if local_idx_dev is not None else torch.as_tensor(
@@ -152,12 +177,9 @@ class PamEngine:
                           ptr(self.prop.traces), stream_ptr())
             else:
                 self.prop.X[0].copy_(self.data.X[idx[0]])
+            torch.add(idx[:1], sh.offset, out=self.prop_idx)
         if sh.size > 1:
-            if self.is_rmsd:
-                self.comm.broadcast(self.prop.xyz, owner)
-                self.comm.broadcast(self.prop.traces, owner)
-            else:
-                self.comm.broadcast(self.prop.X, owner)
+            self.comm.broadcast(self.prop_buf, owner)
 
     # -- one sweep -----------------------------------------------------------------------
     def sweep(self, proposals=None, random_state=None, striped_randind=False, log=None,
@@ -218,11 +240,11 @@ class PamEngine:
             _lib.call("eb_pam_classify", ptr(d), ptr(self.dist), ptr(self.assign), self.n,
                       int(not self.is_rmsd), cid, ptr(self.new_dist), ptr(self.new_assign),
                       ptr(self.ambig_idx), ptr(self.scal_i[1:]), stream_ptr())
+            self.scal_i[:1].copy_(self.prop_idx)
             scal = self.scal_i.cpu()
             n_ambig = int(scal[1])
             if prop_global is None:
-                mine = int(scal[0]) + sh.offset if sh.rank == owner else -1
-                prop_global = max(self.comm.all_gather_object(mine)) if sh.size > 1 else mine
+                prop_global = int(scal[0])
 
             t = tick("classify+readback", t)
             # ---- ambiguous frames against all medoids, proposal in slot cid (:660-670) --

@@ -38,7 +38,7 @@ constexpr int B_TILE = BN * BK * 4;      // 6144
 constexpr int STAGE_BYTES = 6 * A_TILE + 2 * B_TILE;  // {hi,lo} x 3 coords of A, {hi,lo} of B
 constexpr int TMEM_COLS = 512;           // 3 accumulators x 144 columns = 432 -> power of two
 constexpr int THREADS = 64 + 128 * 2;  // producer, MMA, 8 epilogue warps
-constexpr int CAND_BUDGET = 256;  // candidate entries per frame, shared out over its lists
+constexpr int CAND_BUDGET = 512;  // candidate entries per frame, shared out over its lists
 constexpr int MIN_CAND = 8;       // ... but never fewer than this per list
 constexpr int DEF_SEG = 4;     // centre segments: CTAs sharing a frame tile hit it in L2
 constexpr int MAX_SEG = 32;    // small frame subsets (PAM) are spread over more segments
@@ -734,10 +734,10 @@ int eb_rmsd_assign_tc(const float *xyz_soa, const double *traces, int64_t n, int
     {
         const size_t list_bytes = align16(sizeof(int) * tc::RS_GROUPS * n_lists * max_cand);
         const size_t stage_bytes = sizeof(float) * tc::RS_GROUPS * 3 * (size_t)A_pad;
-        static int rs_mode = -1;   // developer A/B switch: EB_RS_STAGE=0 forces the unstaged path
+        static int rs_mode = -1;   // developer A/B switch: EB_RS_STAGE=1 stages frames in smem
         if (rs_mode < 0) {
             const char *e = getenv("EB_RS_STAGE");
-            rs_mode = e ? atoi(e) : 1;
+            rs_mode = e ? atoi(e) : 0;   // measured: 6.6 ms unstaged vs 7.5 ms staged
         }
         const bool stage = rs_mode != 0 && list_bytes + stage_bytes <= 113 * 1024;  // 2 blocks/SM
         const size_t rs_smem = list_bytes + (stage ? stage_bytes : 0);

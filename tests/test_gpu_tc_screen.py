@@ -48,19 +48,19 @@ def test_tc_assign_matches_oracle(cuda):
 
 
 def test_tc_overflow_falls_back_to_exact(cuda):
-    """Many identical centres -> a candidate list (32 entries; a list covers 48 centres here)
+    """Many identical centres -> a candidate list (64 entries; a list covers 120 centres here)
     overflows for every frame -> exact fallback, same result."""
     from enspara_b200 import synth
     from enspara_b200.cluster import _ops, util
     from enspara_b200.device import DeviceTrajectory
     data = DeviceTrajectory.from_host(synth.trajectory(9600, 64, seed=2))
-    cen = data.gather(np.array([5] * 192 + [17] * 192, dtype=np.int64))
+    cen = data.gather(np.array([5] * 400 + [17] * 400, dtype=np.int64))
     d0, a0 = _ops.assign_device(util.RMSD, data, cen)
     stats = {}
     d1, a1 = _ops.assign_device_tc(util.RMSD, data, cen, stats=stats)
     assert stats["overflow_frames"] > 0
     assert cuda.equal(a0, a1) and cuda.equal(d0, d1)
-    assert set(np.unique(a1.cpu().numpy())) <= {0, 192}     # lowest index among duplicates
+    assert set(np.unique(a1.cpu().numpy())) <= {0, 400}     # lowest index among duplicates
 
 
 @pytest.mark.parametrize("n,A,k,m", [(6000, 500, 200, 700), (3000, 48, 1000, 37),
