@@ -54,6 +54,40 @@ def main():
         [int(c) for c in serial.center_indices]
     ok &= np.array_equal(shard.assignments, serial.assignments[bounds[rank]:bounds[rank + 1]])
     ok &= np.array_equal(shard.distances, serial.distances[bounds[rank]:bounds[rank + 1]])
+    # the `cluster` app under torchrun: file i on rank i % size, results re-assembled on every
+    # rank, rank 0 writes -- must equal the serial estimator (test_apps_cluster_mpi.py:100-139)
+    import tempfile
+    from enspara_b200 import ra
+    from enspara_b200.apps import cluster as app
+    from enspara_b200.cluster import KCenters
+    tmp = os.environ.get("EB_MGPU_TMP") or tempfile.gettempdir()
+    G = synth.features(4 * 300, 6, seed=9)
+    files = [os.path.join(tmp, "eb_mgpu_f%d.npy" % i) for i in range(2 * size)]
+    cuts = np.linspace(0, len(G), 2 * size + 1).astype(int)
+    if rank == 0:
+        for i, f in enumerate(files):
+            np.save(f, G[cuts[i]:cuts[i + 1]])
+    dist.barrier()
+    outs = {k: os.path.join(tmp, "eb_mgpu_%s" % k) for k in
+            ("dist.h5", "assig.h5", "ctrs.npy", "inds.npy")}
+    rc = app.main(["cluster", "--features"] + files + [
+        "--algorithm", "kcenters", "--cluster-distance", "euclidean", "--cluster-radius", "0.7",
+        "--distances", outs["dist.h5"], "--assignments", outs["assig.h5"],
+        "--center-features", outs["ctrs.npy"], "--center-indices", outs["inds.npy"]])
+    ok &= rc == 0
+    dist.barrier()
+    if rank == 0:
+        serial = KCenters("euclidean", cluster_radius=0.7, mpi_mode=False).fit(G)
+        d = ra.load(outs["dist.h5"])
+        a = ra.load(outs["assig.h5"])
+        dflat = d.flatten() if hasattr(d, "flatten") and not isinstance(d, np.ndarray) \
+            else np.asarray(d).reshape(-1)
+        aflat = a.flatten() if hasattr(a, "flatten") and not isinstance(a, np.ndarray) \
+            else np.asarray(a).reshape(-1)
+        ok &= np.array_equal(dflat, serial.distances_)
+        ok &= len(np.unique(aflat)) == len(serial.center_indices_)
+        ctrs = np.load(outs["ctrs.npy"])
+        ok &= ctrs.shape == (len(serial.center_indices_), 6)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

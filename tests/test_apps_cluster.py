@@ -89,3 +89,61 @@ def test_feature_clustering_end_to_end(tmp_path):
     assert rc == 0
     r = ra.load(os.path.join(t, "assig.npy.npz"))
     assert [len(x) for x in r] == [30, 70] and len(np.unique(r.flatten())) == 4
+
+
+@pytest.mark.gpu
+def test_h5_io_intermediates_and_kmedoids_restart(tmp_path):
+    """.h5 outputs / inputs without PyTables (test_apps_cluster.py:26-92 checks these files with
+    ra.load), --save_intermediates (hybrid.py:129-151, kmedoids.py:459-473) and the k-medoids
+    restart flags (apps/cluster.py:136-147, 317-329)."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from sklearn.datasets import make_blobs
+    from enspara_b200 import ra
+    from enspara_b200.cluster import KHybrid, KMedoids
+    t = str(tmp_path)
+    X, _ = make_blobs(n_samples=120, n_features=4, random_state=5)
+    rows = ra.RaggedArray([X[:50], X[50:]])
+    ra.save(os.path.join(t, "feat.h5"), rows)                 # ragged features in one .h5
+    out = ["--distances", os.path.join(t, "dist.h5"), "--assignments", os.path.join(t, "assig.h5"),
+           "--center-features", os.path.join(t, "ctrs.npy"),
+           "--center-indices", os.path.join(t, "inds.npy")]
+    rc = app.main(["cluster", "--features", os.path.join(t, "feat.h5")] + out + [
+        "--algorithm", "khybrid", "--cluster-distance", "euclidean", "--cluster-number", "5",
+        "--cluster-iterations", "2", "--save_intermediates", "True"])
+    assert rc == 0
+    assig = ra.load(os.path.join(t, "assig.h5"))
+    dist = ra.load(os.path.join(t, "dist.h5"))
+    assert isinstance(assig, ra.RaggedArray) and list(assig.lengths) == [50, 70]
+    assert assig.dtype == np.int64 and dist.dtype == np.float64
+    direct = KHybrid("euclidean", n_clusters=5, kmedoids_updates=2).fit(X)
+    assert len(np.unique(assig.flatten())) == 5
+    assert dist.flatten().shape == direct.distances_.shape
+    # intermediates: after k-centers and after the first of the two sweeps
+    for tag in ("kcenters", "kmedoids-0"):
+        d = os.path.join(t, "intermediate-%s" % tag)
+        assert sorted(os.listdir(d)) == ["assig.h5", "ctrs.npy", "dist.h5", "inds.npy"], tag
+        assert list(ra.load(os.path.join(d, "assig.h5")).lengths) == [50, 70]
+    # the k-centers intermediate equals a plain k-centers run
+    from enspara_b200.cluster import KCenters
+    kc = KCenters("euclidean", n_clusters=5).fit(X)
+    assert_array_equal(ra.load(os.path.join(t, "intermediate-kcenters", "dist.h5")).flatten(),
+                       kc.distances_)
+
+    # restart k-medoids from these results (files written by the run above)
+    np.save(os.path.join(t, "a.npy"), X[:50])
+    np.save(os.path.join(t, "b.npy"), X[50:])
+    # ... exactly as a user would: the previous run's .h5 / .npy outputs are the init files
+    os.replace(os.path.join(t, "assig.h5"), os.path.join(t, "init_assig.h5"))
+    os.replace(os.path.join(t, "dist.h5"), os.path.join(t, "init_dist.h5"))
+    os.replace(os.path.join(t, "inds.npy"), os.path.join(t, "init_inds.npy"))
+    rc = app.main(_argv(t, ["--algorithm", "kmedoids", "--cluster-distance", "euclidean",
+                            "--cluster-number", "5", "--cluster-iterations", "1",
+                            "--init-assignments", os.path.join(t, "init_assig.h5"),
+                            "--init-distances", os.path.join(t, "init_dist.h5"),
+                            "--init-center-inds", os.path.join(t, "init_inds.npy")]))
+    assert rc == 0
+    d2 = ra.load(os.path.join(t, "dist.npy.npz")).flatten()
+    # a PAM sweep never increases the mean-square cost
+    assert np.mean(d2 ** 2) <= np.mean(dist.flatten() ** 2) + 1e-12
