@@ -351,6 +351,15 @@ k_tc_screen(const unsigned char *__restrict__ a_img, const unsigned char *__rest
                         tc_ld8(lane_addr + col + 16, &m[i][16]);
                     }
                     tc_wait_ld();
+                    if (MODE == 2) {
+                        // timing probe (mode 2): consume the accumulators without the QCP
+                        float acc = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 3; ++i)
+#pragma unroll
+                            for (int j = 0; j < 24; ++j) acc += m[i][j];
+                        if (acc == 1.2345e-30f && dbg) dbg[0] = acc;
+                    }
                     if (MODE == 0) {
 #pragma unroll
                         for (int cc = 0; cc < 8; ++cc) {
@@ -364,7 +373,7 @@ k_tc_screen(const unsigned char *__restrict__ a_img, const unsigned char *__rest
                         }
                     }
 #pragma unroll
-                    for (int bq = 0; bq < (MODE == 0 ? 0 : 2); ++bq) {   // two batches of four
+                    for (int bq = 0; bq < (MODE == 1 ? 2 : 0); ++bq) {   // two batches of four
                         float Mn[4][9], gq[4], scf[4], lam[4], dl[4];
                         double Gb[4];
 #pragma unroll
@@ -465,15 +474,17 @@ k_tc_screen(const unsigned char *__restrict__ a_img, const unsigned char *__rest
 // ---- exact re-scoring of the surviving (frame, centre) pairs ---------------------------------
 // A group of 8 lanes owns one frame: it merges the frame's candidate lists (global upper bound
 // U = min over lists; survivors = entries whose lower bound does not exceed U) into one compact
-// list in shared memory, stages the frame's coordinates in shared memory once, and then scores
-// two centres per pass with the exact float64 arithmetic of the reference path (float x float
-// products are exact in double; QCP in double; float32 result).  Ties: lowest centre index, which
-// is what strict '<' in centre order gives (cluster/util.py:201).  Centres come from L2.
+// list in shared memory and then scores two centres per pass (the frame's loads and conversions
+// are shared) with the exact float64 arithmetic of the reference path (float x float products
+// are exact in double; QCP in double; float32 result).  Ties: lowest centre index, which is what
+// strict '<' in centre order gives (cluster/util.py:201).  Frame and centres come from L1/L2.
+// Measured alternatives (262144 frames x 1008 centres, 7.8 survivors per frame): this kernel
+// 6.1 ms; frame staged in shared memory (2 blocks/SM) 7.5 ms; centres prefetched with
+// cp.async.bulk into per-group double buffers (4 warps/SM, frame from L2) 14.1 ms.
 constexpr int RS_GROUPS = 16;            // frames per block
 constexpr int RS_THREADS = RS_GROUPS * 8;
 
-template <bool STAGE>
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, 5)
 k_rescore(const float *__restrict__ xyz, const double *__restrict__ traces, long n, int n_atoms,
           int A_pad, const float *__restrict__ centers, const double *__restrict__ ctraces,
           const int *__restrict__ cand_count, const int *__restrict__ cand_list,
@@ -484,13 +495,11 @@ k_rescore(const float *__restrict__ xyz, const double *__restrict__ traces, long
     extern __shared__ __align__(16) unsigned char rs_smem[];
     const int list_cap = n_seg * MAX_CAND;
     int *cl_all = reinterpret_cast<int *>(rs_smem);                       // [RS_GROUPS][list_cap]
-    float *fr_all = reinterpret_cast<float *>(rs_smem + align16(sizeof(int) * RS_GROUPS * list_cap));
     const int lane = threadIdx.x & 31, g = lane >> 3, l8 = lane & 7;
     const int grp = threadIdx.x >> 3;                                    // group within the block
     const int A4 = A_pad >> 2;
     const size_t stride = 3 * (size_t)A_pad;
     int *cl = cl_all + (size_t)grp * list_cap;
-    float *fr = fr_all + (size_t)grp * stride;
     const long groups = (long)gridDim.x * RS_GROUPS;
     const long n_round = (n + groups - 1) / groups * groups;   // every warp runs the same trips
     for (long fb = (long)blockIdx.x * RS_GROUPS + grp; fb < n_round; fb += groups) {
@@ -513,10 +522,6 @@ k_rescore(const float *__restrict__ xyz, const double *__restrict__ traces, long
         const bool overflow = ovf != 0;
         const long src = valid ? (frame_idx ? (long)frame_idx[f] : f) : 0;  // row of xyz / traces
         const float4 *px = reinterpret_cast<const float4 *>(xyz + (size_t)src * stride);
-        if (STAGE && valid && !overflow) {
-            float4 *dst = reinterpret_cast<float4 *>(fr);
-            for (int t = l8; t < 3 * A4; t += 8) dst[t] = __ldg(px + t);
-        }
         // compact the survivors of all lists into cl[0 .. cnt_g)
         int cnt_g = 0;
         for (int sgm = 0; sgm < n_seg; ++sgm) {
@@ -542,7 +547,6 @@ k_rescore(const float *__restrict__ xyz, const double *__restrict__ traces, long
         float best_d = INFINITY;
         int best_c = 0;
         const double Ga = valid ? traces[src] : 0.0;
-        const float4 *sx = STAGE ? reinterpret_cast<const float4 *>(fr) : px;
         for (int i0 = 0; i0 < tmax; i0 += 2) {
             const bool act0 = i0 < cnt_g, act1 = i0 + 1 < cnt_g;
             const int c0 = act0 ? cl[i0] : 0, c1 = act1 ? cl[i0 + 1] : c0;
@@ -552,7 +556,8 @@ k_rescore(const float *__restrict__ xyz, const double *__restrict__ traces, long
             if (act0) {
 #pragma unroll 2
                 for (int j = l8; j < A4; j += 8) {
-                    const float4 x = sx[j], y = sx[A4 + j], z = sx[2 * A4 + j];
+                    const float4 x = __ldg(px + j), y = __ldg(px + A4 + j),
+                                 z = __ldg(px + 2 * A4 + j);
                     const float4 ax = __ldg(p0 + j), ay = __ldg(p0 + A4 + j),
                                  az = __ldg(p0 + 2 * A4 + j);
                     const float4 bx = __ldg(p1 + j), by = __ldg(p1 + A4 + j),
@@ -723,6 +728,16 @@ int eb_rmsd_assign_tc(const float *xyz_soa, const double *traces, int64_t n, int
         EB_LAUNCH_CHECK();
         return EB_OK;
     }
+    if (mode == 2) {   // timing probe: the screen without its QCP epilogue
+        EB_CUDA(cudaFuncSetAttribute(tc::k_tc_screen<2>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc::k_tc_screen<2><<<grid, tc::THREADS, smem, s>>>(a_img, b_img, traces,
+                                                           center_traces, n, k, n_atoms, A_pad,
+                                                           kappa, dbg, nullptr, nullptr, nullptr,
+                                                           nullptr, n_seg, frame_idx, 8);
+        EB_LAUNCH_CHECK();
+        return EB_OK;
+    }
     EB_CHECK_ARG(out_dist && out_assign && cand_count, "rmsd_assign_tc: null output");
     EB_CUDA(cudaFuncSetAttribute(tc::k_tc_screen<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
@@ -732,22 +747,13 @@ int eb_rmsd_assign_tc(const float *xyz_soa, const double *traces, int64_t n, int
                                                        cand_umin, n_seg, frame_idx, max_cand);
     EB_LAUNCH_CHECK();
     {
-        const size_t list_bytes = align16(sizeof(int) * tc::RS_GROUPS * n_lists * max_cand);
-        const size_t stage_bytes = sizeof(float) * tc::RS_GROUPS * 3 * (size_t)A_pad;
-        static int rs_mode = -1;   // developer A/B switch: EB_RS_STAGE=1 stages frames in smem
-        if (rs_mode < 0) {
-            const char *e = getenv("EB_RS_STAGE");
-            rs_mode = e ? atoi(e) : 0;   // measured: 6.6 ms unstaged vs 7.5 ms staged
-        }
-        const bool stage = rs_mode != 0 && list_bytes + stage_bytes <= 113 * 1024;  // 2 blocks/SM
-        const size_t rs_smem = list_bytes + (stage ? stage_bytes : 0);
+        const size_t rs_smem = align16(sizeof(int) * tc::RS_GROUPS * n_lists * max_cand);
         long blocks = (n + tc::RS_GROUPS - 1) / tc::RS_GROUPS;
-        if (blocks > 8L * sm_count()) blocks = 8L * sm_count();
-        auto kern = stage ? tc::k_rescore<true> : tc::k_rescore<false>;
+        if (blocks > 10L * sm_count()) blocks = 10L * sm_count();
         EB_CHECK_ARG(rs_smem <= 227 * 1024, "rmsd_assign_tc: candidate lists too large");
-        EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        EB_CUDA(cudaFuncSetAttribute(tc::k_rescore, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)rs_smem));
-        kern<<<(int)blocks, tc::RS_THREADS, rs_smem, s>>>(
+        tc::k_rescore<<<(int)blocks, tc::RS_THREADS, rs_smem, s>>>(
             xyz_soa, traces, n, n_atoms, A_pad, centers_soa, center_traces, seg_count, cand_list,
             cand_bound, cand_umin, (int)n_lists, out_dist, out_assign, cand_count, frame_idx,
             scatter, max_cand);

@@ -182,7 +182,8 @@ int eb_feat_one_to_all(const void *X, int64_t n, int64_t n_features, int dtype, 
  * cand_count is indexed by position, results go to position i or, with `scatter`, to
  * frame_idx[i].  scratch: eb_tc_scratch_bytes(n, n_atoms, k).  Any n_atoms (the packed
  * operand images are zero-padded to a multiple of 16 atoms).  mode 0 is a debugging aid: dbg (n*k*9 floats) receives the
- * approximate inner-product matrices and nothing else is written. */
+ * approximate inner-product matrices and nothing else is written; mode 2 is a timing probe
+ * (pack + screen with the QCP epilogue removed; no outputs). */
 size_t eb_tc_scratch_bytes(int64_t n, int n_atoms, int32_t k);
 int eb_rmsd_assign_tc(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
                       const float *centers_soa, const double *center_traces, int32_t k,
