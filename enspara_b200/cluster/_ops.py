@@ -38,7 +38,7 @@ def _single_frame_soa(metric, y, like):
     return DeviceFeatures.from_host(arr[None])
 
 
-def one_to_all_device(metric, data, center, exact=True, out=None, **_unused):
+def one_to_all_device(metric, data, center, exact=True, out=None):
     """Distances of every frame of ``data`` to the single frame ``center`` as a device tensor
     (float32 for RMSD like md.rmsd, float64 for libdist metrics).  No host synchronisation."""
     n = len(data)

@@ -15,6 +15,8 @@ member is counted in GLOBAL frame order, which makes a sharded run equal to the 
 (the reference's ``mpi.ops.randind`` maps the draw through a striped concatenation instead,
 mpi/ops.py:256-268; that alternative map is available as ``striped_randind=True``).
 """
+import time
+
 import numpy as np
 import torch
 from sklearn.utils import check_random_state
@@ -196,8 +198,7 @@ class PamEngine:
             if prof is None:
                 return 0.0
             torch.cuda.synchronize()
-            import time as _t
-            now = _t.perf_counter()
+            now = time.perf_counter()
             if name:
                 prof[name] = prof.get(name, 0.0) + now - t0
             return now
@@ -235,7 +236,7 @@ class PamEngine:
             t = tick("proposal", t)
             # ---- full pass + three-way split (kmedoids.py:637-658) -------------------
             d = _ops.one_to_all_device(self.metric, self.data, self.prop,
-                                       center_trace_dev=True, out=self.new_ctr_dist)
+                                       out=self.new_ctr_dist)
             t = tick("full_pass", t)
             _lib.call("eb_pam_classify", ptr(d), ptr(self.dist), ptr(self.assign), self.n,
                       int(not self.is_rmsd), cid, ptr(self.new_dist), ptr(self.new_assign),
