@@ -54,6 +54,8 @@ SIGNATURES = {
     "eb_kcenters_seed_feat": (_int, [_vp, _i64, _i64, _int, _i64, _vp, _i32, _vp, _vp, _vp,
                                      _vp]),
     "eb_feat_one_to_all": (_int, [_vp, _i64, _i64, _int, _int, _vp, _vp, _vp]),
+    "eb_rmsd_one_to_all_pruned": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _i32,
+                                         _vp, _vp]),
     "eb_rmsd_assign": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _int,
                               _int, _vp]),
     "eb_tc_scratch_bytes": (_sz, [_i64, _int, _i32]),

@@ -68,6 +68,10 @@ class PamEngine:
         self.use_tc = self.is_rmsd and _ops.tc_applicable(metric, data, self.k)
         self._tc_ws = {}
         self.profile = None
+        # triangle-inequality pruning of the full pass (RMSD is a metric): frames that provably
+        # stay with their medoid are not read; the sweep's result is unchanged
+        self.prune = self.is_rmsd and self.k >= 2
+        self.cc = torch.zeros(max(self.k, 1), dtype=torch.float32, device=dev)
 
     # -- helpers -------------------------------------------------------------------------
     def _to_dev(self, arr, dtype):
@@ -235,8 +239,17 @@ class PamEngine:
 
             t = tick("proposal", t)
             # ---- full pass + three-way split (kmedoids.py:637-658) -------------------
-            d = _ops.one_to_all_device(self.metric, self.data, self.prop,
-                                       out=self.new_ctr_dist)
+            if self.prune:
+                # distances proposal -> every medoid (k evaluations), then the pruned pass
+                _ops.one_to_all_device(self.metric, self.medoids, self.prop, out=self.cc)
+                d = self.new_ctr_dist
+                _lib.call("eb_rmsd_one_to_all_pruned", ptr(self.data.xyz),
+                          ptr(self.data.traces), self.n, self.data.n_atoms, ptr(self.prop.xyz),
+                          ptr(self.prop.traces), ptr(self.dist), ptr(self.assign), ptr(self.cc),
+                          cid, ptr(d), stream_ptr())
+            else:
+                d = _ops.one_to_all_device(self.metric, self.data, self.prop,
+                                           out=self.new_ctr_dist)
             t = tick("full_pass", t)
             _lib.call("eb_pam_classify", ptr(d), ptr(self.dist), ptr(self.assign), self.n,
                       int(not self.is_rmsd), cid, ptr(self.new_dist), ptr(self.new_assign),

@@ -229,6 +229,21 @@ k_kcenters_step_rmsd(const float *__restrict__ xyz, const double *__restrict__ t
             }
             need_mask = __ballot_sync(0xffffffffu, need);
         }
+        if (VAR == kVarTri && MODE == kModeDistOnly) {
+            // PAM full pass: a frame of another cluster whose distance to its medoid is at most
+            // (1 - 1e-5)/2 of that medoid's distance to the proposal cannot get closer to the
+            // proposal than it is to its medoid (triangle inequality; the margin keeps the
+            // float32 rounding of both distances, ~1e-7 relative, out of the decision), so the
+            // split of kmedoids.py:644-658 leaves it untouched: report +inf, do not read it.
+            // n_clusters_limit carries the proposal's cluster id.
+            bool need = false;
+            if (f < n) {
+                const int a = assign[f];
+                need = (a < 0) || (a == n_clusters_limit) ||
+                       !(dist[f] <= 0.499995f * __ldg(cc + a));
+            }
+            need_mask = __ballot_sync(0xffffffffu, need);
+        }
         if (MODE != kModeSeed) {
 #pragma unroll 1
             for (int s = 0; s < 8; ++s) {
@@ -263,6 +278,9 @@ k_kcenters_step_rmsd(const float *__restrict__ xyz, const double *__restrict__ t
                 cur = (double)dist[f];
             } else if (VAR == kVarTri && MODE == kModeStep && !((need_mask >> lane) & 1u)) {
                 cur = (double)tri_old;     // pruned: distance and assignment stay
+            } else if (VAR == kVarTri && MODE == kModeDistOnly && !((need_mask >> lane) & 1u)) {
+                out_only[f] = INFINITY;    // pruned: provably not closer to the proposal
+                cur = 0.0;
             } else {
                 double m[9];
                 const double *src = my_sums + lane * kSumStride;
@@ -568,6 +586,28 @@ int eb_rmsd_one_to_all(const float *xyz_soa, const double *traces, int64_t n, in
                                              nullptr, 0, 0.0, nullptr, nullptr, nullptr, nullptr,
                                              center_soa, center_trace, out,
                                              (cudaStream_t)stream);
+}
+
+// One-vs-all distances for a PAM proposal with triangle-inequality pruning: out[f] = +inf (and
+// frame f is not read) when assign[f] != cid and dist[f] <= (1 - 1e-5)/2 * cc[assign[f]], where
+// cc[j] = d(proposal, medoid j).  For every other frame out[f] is exactly what
+// eb_rmsd_one_to_all writes.  The three-way split of kmedoids.py:644-658 classifies a pruned
+// frame as "unchanged", which is what its true distance would do.
+int eb_rmsd_one_to_all_pruned(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
+                              const float *center_soa, const double *center_trace,
+                              const float *dist, const int32_t *assign, const float *cc,
+                              int32_t cid, float *out, void *stream)
+{
+    EB_CHECK_ARG(n >= 0 && n_atoms > 0, "rmsd_one_to_all_pruned: bad shape");
+    if (n == 0) return EB_OK;
+    EB_CHECK_ARG(xyz_soa && traces && center_soa && center_trace && out && dist && assign && cc,
+                 "rmsd_one_to_all_pruned: null pointer");
+    StepExtra ex;
+    ex.cc = const_cast<float *>(cc);
+    return launch_step_v<true, kModeDistOnly, kVarTri>(
+        xyz_soa, traces, n, n_atoms, 0, nullptr, 0, const_cast<float *>(dist),
+        const_cast<int32_t *>(assign), cid, 0.0, nullptr, nullptr, nullptr, nullptr, center_soa,
+        center_trace, out, (cudaStream_t)stream, ex);
 }
 
 }  // extern "C"

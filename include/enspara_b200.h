@@ -170,6 +170,16 @@ int eb_kcenters_seed_feat(const void *X, int64_t n, int64_t n_features, int dtyp
 int eb_feat_one_to_all(const void *X, int64_t n, int64_t n_features, int dtype, int metric,
                        const void *y, double *out, void *stream);
 
+/* md.rmsd(X, proposal) for a PAM proposal (kmedoids.py:637) with triangle-inequality pruning:
+ * out[f] = +inf, and frame f is not read, when assign[f] != cid and
+ * dist[f] <= (1 - 1e-5)/2 * cc[assign[f]] with cc[j] = d(proposal, medoid j); every other
+ * entry equals eb_rmsd_one_to_all's.  The split of kmedoids.py:644-658 leaves a pruned frame
+ * unchanged, exactly as its true distance would. */
+int eb_rmsd_one_to_all_pruned(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
+                              const float *center_soa, const double *center_trace,
+                              const float *dist, const int32_t *assign, const float *cc,
+                              int32_t cid, float *out, void *stream);
+
 /* ---- K3 on the tensor cores: 3xTF32 tcgen05 screen + exact re-score ----------------------
  * Same result as eb_rmsd_assign (dense pass over all n frames, no accumulate): a tcgen05 GEMM
  * with a fused QCP epilogue bounds every (frame, centre) distance; only centres whose lower

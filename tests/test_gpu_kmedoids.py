@@ -223,3 +223,31 @@ def test_kmedoids_input_errors(cuda):
     with pytest.raises(DataInvalid):
         kmedoids._kmedoids_pam_update(X, "euclidean", [0, 1], np.zeros(30, int),
                                       np.zeros(30), proposals=[1, 2, 3])
+
+
+def test_pam_pruned_full_pass_changes_nothing(cuda):
+    """The triangle-inequality pruning of the PAM full pass (frames that provably stay with
+    their medoid are not read) gives bit-identical sweeps."""
+    from enspara_b200 import synth
+    from enspara_b200.cluster import kcenters, util
+    from enspara_b200.cluster._pam import PamEngine
+    from enspara_b200.cluster.kcenters import _SingleComm
+    from enspara_b200.device import DeviceTrajectory
+    for n, A, k in ((6000, 40, 50), (3000, 22, 100), (501, 22, 7)):
+        data = DeviceTrajectory.from_host(synth.trajectory(n, A, seed=n))
+        r = kcenters.kcenters(data, "rmsd", n_clusters=k)
+        ctr = [int(c) for c in r.center_indices]
+        out = []
+        for prune in (True, False):
+            pam = PamEngine(data, util.RMSD, _SingleComm(), r.distances, r.assignments, ctr)
+            assert pam.prune
+            pam.prune = prune
+            log = []
+            for sweep in range(2):
+                pam.sweep(random_state=sweep, log=log)
+            a, d = pam.results_host()
+            out.append((list(pam.medoid_global), a, d, log))
+        assert out[0][0] == out[1][0]
+        assert_array_equal(out[0][1], out[1][1])
+        assert_array_equal(out[0][2], out[1][2])
+        assert out[0][3] == out[1][3]        # same proposals, same costs, same decisions
