@@ -140,7 +140,12 @@ struct StepSmem {
     int64_t center_index;
 };
 
-template <bool EXACT, int MODE, int VAR>
+// ROUNDS: 4-frame rounds per warp chunk (a chunk is 4*ROUNDS consecutive frames).  8 for large
+// shards (32 frames: coalesced 128-byte dist/assign updates); fewer when there are not enough
+// frames to give every resident warp a full chunk (small trajectories, the k stored centres of
+// the triangle mode, PAM's proposal-to-medoids distances), so the per-launch latency is one or
+// two rounds instead of eight.
+template <bool EXACT, int MODE, int VAR, int ROUNDS = 8>
 __global__ void __launch_bounds__(kStepThreads, 2)
 k_kcenters_step_rmsd(const float *__restrict__ xyz, const double *__restrict__ traces, long n,
                      int A, int A_pad, long frame_offset, const unsigned char *cand_in,
@@ -208,14 +213,16 @@ k_kcenters_step_rmsd(const float *__restrict__ xyz, const double *__restrict__ t
     // ---- body -----------------------------------------------------------------------------
     double best_d = -2.0;
     int64_t best_i = INT64_MAX;
-    const long n_chunks = (n + 31) >> 5;
+    constexpr int FPC = 4 * ROUNDS;                     // frames per chunk
+    const long n_chunks = (n + FPC - 1) / FPC;
     const long warps_total = (long)gridDim.x * kStepWarps;
     double *my_sums = sums + (size_t)warp * 32 * kSumStride;
 
     for (long chunk = (long)blockIdx.x * kStepWarps + warp; chunk < n_chunks;
          chunk += warps_total) {
-        const long base = chunk << 5;
-        const long f = base + lane;
+        const long base = chunk * FPC;
+        // lanes beyond the chunk own no frame (ROUNDS < 8)
+        const long f = (lane < FPC) ? base + lane : n;
         // triangle-inequality pruning: lane l decides for frame base + l, the warp shares the
         // decisions as a bit mask; rounds whose four frames are all pruned load nothing
         unsigned need_mask = 0xffffffffu;
@@ -246,14 +253,14 @@ k_kcenters_step_rmsd(const float *__restrict__ xyz, const double *__restrict__ t
         }
         if (MODE != kModeSeed) {
 #pragma unroll 1
-            for (int s = 0; s < 8; ++s) {
+            for (int s = 0; s < ROUNDS; ++s) {
                 if (VAR == kVarTri && ((need_mask >> (4 * s)) & 0xfu) == 0u) continue;
                 const long fs = base + 4 * s + g;
                 double m[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
                 if (VAR == 2) {
                     // software prefetch of the frame this group streams in the next round
                     // (or the first round of the warp's next chunk) into L2
-                    const long fn = (s < 7) ? fs + 4 : ((chunk + warps_total) << 5) + g;
+                    const long fn = (s < ROUNDS - 1) ? fs + 4 : (chunk + warps_total) * FPC + g;
                     if (fn < n) {
                         const char *pn = reinterpret_cast<const char *>(xyz + (size_t)fn * 3 * A_pad);
                         const int n_lines = (12 * A_pad + 127) >> 7;
@@ -347,14 +354,24 @@ static size_t step_smem_bytes(int A_pad)
            sizeof(double) * 3 * (size_t)A_pad;
 }
 
-static int step_grid(long n)
+static int step_grid(long n, int frames_per_chunk = 32)
 {
-    const long chunks = (n + 31) / 32;
+    const long chunks = (n + frames_per_chunk - 1) / frames_per_chunk;
     long blocks = (chunks + kStepWarps - 1) / kStepWarps;
     const long cap = 2L * sm_count();
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     return (int)blocks;
+}
+
+// 4-frame rounds per warp chunk: the largest of 8/4/2/1 that still gives every resident warp
+// (2 CTAs x 8 warps per SM) a chunk
+static int pick_rounds(long n)
+{
+    const long warps = 2L * sm_count() * kStepWarps;
+    int r = 8;
+    while (r > 1 && (n + 4 * r - 1) / (4 * r) < warps) r >>= 1;
+    return r;
 }
 
 static int k1_variant()
@@ -376,6 +393,37 @@ struct StepExtra {
     long grid_frames = -1;   // size the grid for this many frames instead of n (kModeCC)
 };
 
+template <bool EXACT, int MODE, int VAR, int ROUNDS>
+static int launch_step_r(const float *xyz, const double *traces, long n, int A, long frame_offset,
+                         const void *cand_in, int n_cand, float *dist, int *assign,
+                         int n_clusters_limit, double cutoff, eb_kc_state *state,
+                         int64_t *center_list, void *partials, void *cand_out,
+                         const float *center_direct, const double *center_trace_direct,
+                         float *out_only, cudaStream_t stream, StepExtra ex)
+{
+    const int A_pad = rmsd_apad(A);
+    const size_t smem = step_smem_bytes(A_pad);
+    if (smem > 227 * 1024)
+        return fail(EB_ERR_LIMIT, "%s: n_atoms=%ld needs %ld bytes of shared memory (max 232448)",
+                    "rmsd step", (long)A, (long)smem);
+    auto kern = k_kcenters_step_rmsd<EXACT, MODE, VAR, ROUNDS>;
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+        configured = smem;
+    }
+    const size_t rec_bytes = sizeof(RecHeader) + sizeof(float) * 3 * (size_t)A_pad;
+    kern<<<step_grid(ex.grid_frames >= 0 ? ex.grid_frames : n, 4 * ROUNDS), kStepThreads, smem,
+           stream>>>(
+        xyz, traces, n, A, A_pad, frame_offset, (const unsigned char *)cand_in, n_cand, rec_bytes,
+        dist, assign, n_clusters_limit, cutoff, state, center_list, (Partial *)partials,
+        (unsigned char *)cand_out, center_direct, center_trace_direct, out_only, ex.cstore,
+        ex.cstore_traces, ex.cc);
+    EB_LAUNCH_CHECK();
+    return EB_OK;
+}
+
 template <bool EXACT, int MODE, int VAR>
 static int launch_step_v(const float *xyz, const double *traces, long n, int A, long frame_offset,
                        const void *cand_in, int n_cand, float *dist, int *assign,
@@ -384,26 +432,20 @@ static int launch_step_v(const float *xyz, const double *traces, long n, int A, 
                        const float *center_direct, const double *center_trace_direct,
                        float *out_only, cudaStream_t stream, StepExtra ex = StepExtra())
 {
-    const int A_pad = rmsd_apad(A);
-    const size_t smem = step_smem_bytes(A_pad);
-    if (smem > 227 * 1024)
-        return fail(EB_ERR_LIMIT, "%s: n_atoms=%ld needs %ld bytes of shared memory (max 232448)",
-                    "rmsd step", (long)A, (long)smem);
-    auto kern = k_kcenters_step_rmsd<EXACT, MODE, VAR>;
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
-        configured = smem;
+#define EB_STEP_ARGS                                                                              \
+    xyz, traces, n, A, frame_offset, cand_in, n_cand, dist, assign, n_clusters_limit, cutoff,     \
+        state, center_list, partials, cand_out, center_direct, center_trace_direct, out_only,     \
+        stream, ex
+    // short chunks only where they matter: the exact kernels without developer load variants
+    if (EXACT && MODE != kModeSeed && (VAR == 0 || VAR == kVarTri)) {
+        switch (pick_rounds(ex.grid_frames >= 0 ? ex.grid_frames : n)) {
+            case 1: return launch_step_r<EXACT, MODE, (VAR == kVarTri ? kVarTri : 0), 1>(EB_STEP_ARGS);
+            case 2: return launch_step_r<EXACT, MODE, (VAR == kVarTri ? kVarTri : 0), 2>(EB_STEP_ARGS);
+            case 4: return launch_step_r<EXACT, MODE, (VAR == kVarTri ? kVarTri : 0), 4>(EB_STEP_ARGS);
+        }
     }
-    const size_t rec_bytes = sizeof(RecHeader) + sizeof(float) * 3 * (size_t)A_pad;
-    kern<<<step_grid(ex.grid_frames >= 0 ? ex.grid_frames : n), kStepThreads, smem, stream>>>(
-        xyz, traces, n, A, A_pad, frame_offset, (const unsigned char *)cand_in, n_cand, rec_bytes,
-        dist, assign, n_clusters_limit, cutoff, state, center_list, (Partial *)partials,
-        (unsigned char *)cand_out, center_direct, center_trace_direct, out_only, ex.cstore,
-        ex.cstore_traces, ex.cc);
-    EB_LAUNCH_CHECK();
-    return EB_OK;
+    return launch_step_r<EXACT, MODE, VAR, 8>(EB_STEP_ARGS);
+#undef EB_STEP_ARGS
 }
 
 template <bool EXACT, int MODE, typename... Args> static int launch_step(Args... args)
