@@ -147,3 +147,18 @@ def test_h5_io_intermediates_and_kmedoids_restart(tmp_path):
     d2 = ra.load(os.path.join(t, "dist.npy.npz")).flatten()
     # a PAM sweep never increases the mean-square cost
     assert np.mean(d2 ** 2) <= np.mean(dist.flatten() ** 2) + 1e-12
+
+
+def test_main_dispatcher_routes_to_the_apps(tmp_path, monkeypatch):
+    """apps/main.py:6-62: `enspara cluster ...` / `enspara reassign ...`."""
+    from enspara_b200.apps import main as entry
+    from enspara_b200.apps import reassign as rapp
+    seen = {}
+    monkeypatch.setattr(app, "main", lambda argv: seen.setdefault("cluster", argv) and 0)
+    monkeypatch.setattr(rapp, "main", lambda argv: seen.setdefault("reassign", argv) and 0)
+    assert entry.main(["enspara", "cluster", "--algorithm", "kcenters"]) == 0
+    assert seen["cluster"] == ["cluster", "--algorithm", "kcenters"]
+    assert entry.main(["enspara", "reassign", "--centers", "c.pkl"]) == 0
+    assert seen["reassign"] == ["reassign", "--centers", "c.pkl"]
+    with pytest.raises(SystemExit):
+        entry.main(["enspara", "implied"])
