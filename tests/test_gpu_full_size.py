@@ -1,0 +1,77 @@
+"""GPU, BASELINE.json full sizes: the oracle cannot run these in seconds, so parity is checked
+through size-independent properties -- idempotence (re-assigning against the chosen centres
+through a DIFFERENT kernel family reproduces the k-centers state bit for bit), self-assignment of
+every centre, pruned == plain, the stop rule, and a sharded-order-independent checksum."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    if torch.cuda.mem_get_info()[0] < 40e9:
+        pytest.skip("needs 40 GB of free device memory")
+    return torch
+
+
+def test_c4_shard_rmsd_full_size(cuda):
+    """One GPU's shard of config 4 (1.25M frames x 500 atoms, 7.7 GB resident), k = 96."""
+    torch = cuda
+    from enspara_b200 import synth
+    from enspara_b200.cluster import _ops, kcenters, util
+    n, A, k = 1_250_000, 500, 96
+    X = synth.device_trajectory(n, A, seed=0)
+    r, eng = kcenters.kcenters(X, "rmsd", n_clusters=k, _return_engine=True)
+    c = [int(i) for i in r.center_indices]
+    assert len(c) == k and len(set(c)) == k and c[0] == 0
+    a = torch.as_tensor(r.assignments)
+    assert int(a.min()) == 0 and int(a.max()) == k - 1
+    np.testing.assert_array_equal(r.assignments[c], np.arange(k))
+    assert r.distances[c].max() < 1e-4
+    # idempotence across kernel families: tcgen05 screen + exact re-score == fused step state
+    cen = X.gather(torch.as_tensor(c, device="cuda"))
+    d2, a2 = _ops.assign_device_tc(util.RMSD, X, cen)
+    assert torch.equal(a2, eng.assign) and torch.equal(d2, eng.dist)
+    # ... and the exact many-centres kernel on a slice
+    sl = torch.arange(0, n, 97, device="cuda")
+    d3, a3 = _ops.assign_device(util.RMSD, X, cen, frame_idx=sl)
+    assert torch.equal(a3, eng.assign[sl]) and torch.equal(d3, eng.dist[sl])
+    # triangle-inequality pruning changes nothing
+    t = kcenters.kcenters(X, "rmsd", n_clusters=k, use_triangle_inequality=True)
+    assert [int(i) for i in t.center_indices] == c
+    np.testing.assert_array_equal(t.assignments, r.assignments)
+    np.testing.assert_array_equal(t.distances, r.distances)
+    # stop rule: the same run with the final radius as cutoff stops at the same centres
+    radius = float(r.distances.max())
+    s = kcenters.kcenters(X, "rmsd", dist_cutoff=radius)
+    assert [int(i) for i in s.center_indices] == c
+    assert s.distances.max() <= radius
+
+
+def test_c2_features_full_size(cuda):
+    """Config 2 (1M x 64 float32, euclidean), k = 200: bit-exact idempotence and row-level
+    agreement of the fused step with libdist's one-vs-all kernel."""
+    torch = cuda
+    from enspara_b200 import synth
+    from enspara_b200.cluster import kcenters, util
+    n, F, k = 1_000_000, 64, 200
+    X = synth.device_features(n, F, seed=0)
+    r = kcenters.kcenters(X, "euclidean", n_clusters=k)
+    c = [int(i) for i in r.center_indices]
+    assert len(set(c)) == k and c[0] == 0
+    np.testing.assert_array_equal(r.assignments[c], np.arange(k))
+    assert r.distances[c].max() == 0.0
+    rows = X.X[torch.as_tensor(c, device="cuda")].cpu().numpy()
+    a2, d2 = util.assign_to_nearest_center(X, rows, "euclidean")
+    np.testing.assert_array_equal(a2, r.assignments)
+    np.testing.assert_array_equal(d2, r.distances)
+    # the last centre's one-vs-all distances bound every frame's distance from above where it
+    # is assigned to that centre, and equal it there
+    d_last = util.EUCLIDEAN(X, rows[-1])
+    sel = r.assignments == k - 1
+    np.testing.assert_array_equal(d_last[sel], r.distances[sel])
+    assert np.all(d_last[~sel] >= r.distances[~sel])
