@@ -47,19 +47,31 @@ def compute_batches(lengths, batch_size):
     return batch_indices
 
 
-def determine_batch_size(n_atoms, dtype_bytes, frac_mem, device_frac=0.35):
-    """Frames per batch: the reference's host-RAM rule (util.py:570-581), additionally capped
-    so a batch (SoA frames + screen scratch) fits in ``device_frac`` of free HBM."""
+#: beyond this many bytes per batch streaming gains nothing (the loader, the H2D copy and the
+#: kernels already overlap); smaller batches keep the two pinned staging buffers modest
+BATCH_BYTES_CAP = 8 << 30
+
+
+def determine_batch_size(n_atoms, dtype_bytes, frac_mem, device_frac=0.25, largest_file=0):
+    """Frames per batch.  The reference's rule is ``frac_mem`` of host RAM (util.py:570-581);
+    here a batch exists twice on the host (two pinned staging buffers, one being filled while
+    the other is consumed) and once on the device (SoA frames + screen scratch), so it is
+    bounded by ``frac_mem`` x RAM / 2, by ``device_frac`` of free HBM and by BATCH_BYTES_CAP --
+    but never below the largest single file when that still fits the RAM / HBM bounds."""
     import psutil
     bytes_per_frame = n_atoms * 3 * dtype_bytes
-    batch_size = int(psutil.virtual_memory().total * frac_mem / bytes_per_frame)
+    hard = int(psutil.virtual_memory().total * frac_mem / 2 / bytes_per_frame)
     try:
         import torch
         if torch.cuda.is_available():
             free, _ = torch.cuda.mem_get_info()
-            batch_size = min(batch_size, int(free * device_frac / bytes_per_frame))
+            # device bytes per frame: padded SoA copy + AoS staging share + packed screen
+            # operands for the chunk in flight, ~3x the host bytes in the worst case
+            hard = min(hard, int(free * device_frac / (3 * bytes_per_frame)))
     except Exception:  # pragma: no cover
         pass
+    soft = max(int(BATCH_BYTES_CAP // bytes_per_frame), min(int(largest_file), hard))
+    batch_size = min(hard, soft)
     return batch_size, batch_size * bytes_per_frame / 1024 ** 3
 
 
@@ -171,7 +183,8 @@ def batch_reassign(targets, centers, lengths, frac_mem, n_procs=None, stats=None
     cxyz = _centers_xyz(centers)
     n_atoms = cxyz.shape[1]
     DTYPE_BYTES = 4
-    batch_size, batch_gb = determine_batch_size(n_atoms, DTYPE_BYTES, frac_mem)
+    batch_size, batch_gb = determine_batch_size(
+        n_atoms, DTYPE_BYTES, frac_mem, largest_file=max(list(lengths) + [0]))
     logger.info("Batch max size set to %s frames (~%.2f GB, %.1f%% of total RAM).",
                 batch_size, batch_gb, frac_mem * 100)
     if len(lengths) and batch_size < max(lengths):
