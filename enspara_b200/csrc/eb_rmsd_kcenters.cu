@@ -18,6 +18,7 @@
 #include <stdlib.h>
 
 #include "eb_rmsd.cuh"
+#include "eb_tma.cuh"
 
 namespace eb {
 
@@ -348,6 +349,231 @@ k_kcenters_step_rmsd(const float *__restrict__ xyz, const double *__restrict__ t
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// K1, TMA-staged variant of the step: same contract, same arithmetic and the SAME summation
+// order as k_kcenters_step_rmsd<true, kModeStep, 0, 8> (8 lanes per frame, lane l8 adds atoms
+// 4j..4j+3 for j = l8, l8+8, ... in increasing j, butterfly over the 8 lanes), so results are
+// bit-identical.  The LDG version keeps its loads in flight in registers (6 x 16 B per lane at
+// 128 registers, 16 warps/SM ~ 49 KB per SM), which is what bounds it (long_scoreboard, 74.7 %
+// of DRAM peak).  Here every warp owns a two-stage ring of shared-memory buffers; a stage holds
+// one HALF (in atoms) of the four frames of a round: twelve cp.async.bulk copies of 2*A_pad
+// bytes (4 frames x 3 coordinate rows), issued by twelve lanes, one mbarrier.  While the warp
+// (first version; 1.235 ms) -- now ONE 2-D tensor copy (cp.async.bulk.tensor.2d, box = 12 rows
+// x half a row of the (3n x A_pad) matrix).  While the warp
+// accumulates a half out of shared memory the next half is in flight: ~12 KB per warp, 96 KB
+// per SM, and no register is held by a load.  One CTA of 8 warps per SM.
+// ------------------------------------------------------------------------------------------
+// P: parts a coordinate row is cut into (a stage holds A_pad / P atoms of four frames);
+// S: ring depth (S - 1 stages are in flight while one is consumed).
+template <int P, int S>
+__global__ void __launch_bounds__(kStepThreads, 1)
+k_kcenters_step_rmsd_tma(const float *__restrict__ xyz, const double *__restrict__ traces, long n,
+                         int A, int A_pad, long frame_offset, const unsigned char *cand_in,
+                         int n_cand, size_t rec_bytes, float *dist, int *assign,
+                         int n_clusters_limit, double cutoff, eb_kc_state *state,
+                         int64_t *center_list, Partial *partials, unsigned char *cand_out,
+                         const __grid_constant__ CUtensorMap tmap)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int kStagesPerChunk = 8 * P;                       // 8 rounds x P parts
+    const uint32_t part_row_bytes = 4u * (uint32_t)A_pad / P;    // one part of a coordinate row
+    const uint32_t stage_bytes = 12u * part_row_bytes;           // 4 frames x 3 rows
+    unsigned char *ring = smem_raw;                              // [warps][S][stage_bytes]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ring + (size_t)kStepWarps * S * stage_bytes);
+    StepSmem *ss = reinterpret_cast<StepSmem *>(bars + kStepWarps * S);
+    double *sums = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(ss) +
+                                              align16(sizeof(StepSmem)));
+    double *center_base = sums + kStepWarps * 32 * kSumStride;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 3, l8 = lane & 7;
+    const int A4 = A_pad >> 2;
+    const int A4p = A4 / P;                                      // float4 per part of a row
+    unsigned char *my_ring = ring + (size_t)warp * S * stage_bytes;
+    uint64_t *bar = bars + warp * S;
+    if (lane == 0) {
+#pragma unroll
+        for (int b = 0; b < S; ++b) mbar_init(&bar[b], 1);
+        fence_mbar_init();
+        tma_prefetch_desc(&tmap);
+    }
+
+    // ---- prologue: winner among the gathered candidates, stop rule -------------------------
+    int k = 0;
+    CenterSmem cs = center_smem_carve(center_base, A4);
+    double cd;
+    int64_t ci;
+    const int r_win = pick_candidate(cand_in, n_cand, rec_bytes, cd, ci);
+    const bool active = (r_win >= 0) && step_active(state, n_clusters_limit, cd, cutoff, k);
+    if (!active) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            if (!state->done) {
+                state->done = 1;
+                state->maxdist = cd;
+            } else {
+                state->n_noop += 1;
+            }
+        }
+        return;
+    }
+    const unsigned char *rec = cand_in + (size_t)r_win * rec_bytes;
+    const double Gb = __ldcg(&reinterpret_cast<const RecHeader *>(rec)->trace);
+    center_smem_fill(cs, reinterpret_cast<const float *>(rec + sizeof(RecHeader)), A_pad);
+    if (threadIdx.x == 0) {
+        ss->center_index = ci;
+        ss->maxdist = cd;
+    }
+    __syncthreads();
+
+    // ---- body ---------------------------------------------------------------------------------
+    double best_d = -2.0;
+    int64_t best_i = INT64_MAX;
+    const long n_chunks = (n + 31) >> 5;
+    const long warps_total = (long)gridDim.x * kStepWarps;
+    double *my_sums = sums + (size_t)warp * 32 * kSumStride;
+
+    // stage st of chunk c = part (st % P) of the four frames of round (st / P): ONE 2-D tensor
+    // copy, box = 12 rows (4 frames x 3 coordinate rows of the (3n x A_pad) matrix) x one part
+    // of a row; rows past the last frame are zero-filled by the TMA unit.  Nothing is requested
+    // -- and nothing will be waited for -- when the whole round lies beyond frame n.  Stages
+    // are numbered q = 0, 1, ... per warp: buffer q % S, mbarrier phase (q / S) & 1.
+    long i_chunk = (long)blockIdx.x * kStepWarps + warp;   // producer cursor
+    int i_st = 0;
+    unsigned q_issue = 0;
+    auto issue = [&]() {
+        if (i_chunk < n_chunks) {
+            const long f0 = (i_chunk << 5) + 4 * (i_st / P);
+            if (lane == 0 && f0 < n) {
+                const int b = (int)(q_issue % S);
+                mbar_expect_tx(&bar[b], stage_bytes);
+                tma_load_2d(my_ring + (size_t)b * stage_bytes, &tmap, (i_st % P) * (A_pad / P),
+                            (int)(f0 * 3), &bar[b]);
+            }
+            ++q_issue;
+            if (++i_st == kStagesPerChunk) {
+                i_st = 0;
+                i_chunk += warps_total;
+            }
+        }
+    };
+#pragma unroll
+    for (int pre = 0; pre < S - 1; ++pre) issue();
+
+    unsigned q = 0;                                        // consumer stage number
+    for (long chunk = (long)blockIdx.x * kStepWarps + warp; chunk < n_chunks;
+         chunk += warps_total) {
+        const long base = chunk << 5;
+        double m[9];
+#pragma unroll 1
+        for (int st = 0; st < kStagesPerChunk; ++st, ++q) {
+            const int b = (int)(q % S);
+            const int part = st % P;
+            // the buffer consumed in the previous stage is free (all lanes are past its
+            // __syncwarp): request the stage S - 1 ahead into it
+            issue();
+            const long f0 = base + 4 * (st / P);
+            if (f0 < n) mbar_wait(&bar[b], (q / S) & 1u);
+            if (part == 0) {
+#pragma unroll
+                for (int e = 0; e < 9; ++e) m[e] = 0.0;
+            }
+            const long fs = f0 + g;
+            if (fs < n) {
+                // rows of this group's frame in the stage: pitch = one part of a row
+                const float4 *px = reinterpret_cast<const float4 *>(
+                    my_ring + (size_t)b * stage_bytes + (size_t)(3 * g) * part_row_bytes);
+                const float4 *py = px + A4p;
+                const float4 *pz = py + A4p;
+                const int lo = part * A4p, hi = lo + A4p;
+                // first j >= lo with j == l8 (mod 8): the LDG kernel's per-lane order
+                int j = lo + ((l8 - lo) & 7);
+#pragma unroll 2
+                for (; j < hi; j += 8) {
+                    const int jj = j - lo;
+                    const float4 x = px[jj], y = py[jj], z = pz[jj];
+                    const double2 cxl = cs.lo[0][j], cxh = cs.hi[0][j];
+                    const double2 cyl = cs.lo[1][j], cyh = cs.hi[1][j];
+                    const double2 czl = cs.lo[2][j], czh = cs.hi[2][j];
+                    acc_atom(m, x.x, y.x, z.x, cxl.x, cyl.x, czl.x);
+                    acc_atom(m, x.y, y.y, z.y, cxl.y, cyl.y, czl.y);
+                    acc_atom(m, x.z, y.z, z.z, cxh.x, cyh.x, czh.x);
+                    acc_atom(m, x.w, y.w, z.w, cxh.y, cyh.y, czh.y);
+                }
+            }
+            if (part == P - 1) {
+                group8_reduce(m);
+                if (l8 == 0) {
+                    double *dst = my_sums + (4 * (st / P) + g) * kSumStride;
+#pragma unroll
+                    for (int e = 0; e < 9; ++e) dst[e] = m[e];
+                }
+            }
+            __syncwarp();
+        }
+        const long f = base + lane;
+        if (f < n) {
+            double mm[9];
+            const double *src = my_sums + lane * kSumStride;
+#pragma unroll
+            for (int e = 0; e < 9; ++e) mm[e] = src[e];
+            const float d = rmsd_from_msd(qcp_msd(mm, traces[f], Gb, A));
+            const float old = dist[f];
+            if (d < old) {  // strict '<', kcenters.py:304
+                dist[f] = d;
+                assign[f] = k;
+            }
+            const double cur = (double)((d < old) ? d : old);
+            if (cur > best_d) {
+                best_d = cur;
+                best_i = f;
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- epilogue: shard arg-max, candidate record, centre list ----------------------------
+    if (!grid_argmax_last_block(best_d, best_i, partials, state, ss->red, &ss->flag)) return;
+
+    RecHeader *out = reinterpret_cast<RecHeader *>(cand_out);
+    const bool empty = (best_i == INT64_MAX);
+    if (!empty) {
+        const float4 *src = reinterpret_cast<const float4 *>(xyz + (size_t)best_i * 3 * A_pad);
+        float4 *dst = reinterpret_cast<float4 *>(cand_out + sizeof(RecHeader));
+        for (int t = threadIdx.x; t < 3 * A4; t += blockDim.x) dst[t] = __ldcg(src + t);
+    }
+    if (threadIdx.x == 0) {
+        out->dist = empty ? -1.0 : best_d;
+        out->index = empty ? -1 : frame_offset + best_i;
+        out->trace = empty ? 0.0 : traces[best_i];
+        out->reserved = 0;
+        center_list[k] = ss->center_index;
+        state->n_centers = k + 1;
+        state->last_center = ss->center_index;
+        state->maxdist = ss->maxdist;
+        state->local_maxdist = empty ? -1.0 : best_d;
+        state->blocks_done = 0;
+        __threadfence();
+    }
+}
+
+static size_t step_tma_smem_bytes(int A_pad, int P, int S)
+{
+    return (size_t)kStepWarps * S * 12 * (4 * (size_t)A_pad / P) +
+           sizeof(uint64_t) * kStepWarps * S + align16(sizeof(StepSmem)) +
+           sizeof(double) * kStepWarps * 32 * kSumStride + sizeof(double) * 3 * (size_t)A_pad;
+}
+
+// TMA-staged kernel for large shards (default); EB_K1_TMA=0 forces the LDG kernel (A/B switch)
+static int k1_tma_enabled()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("EB_K1_TMA");
+        v = e ? atoi(e) : 1;
+    }
+    return v;
+}
+
 static size_t step_smem_bytes(int A_pad)
 {
     return align16(sizeof(StepSmem)) + sizeof(double) * kStepWarps * 32 * kSumStride +
@@ -538,6 +764,45 @@ int eb_kcenters_step_rmsd(const float *xyz_soa, const double *traces, int64_t n,
     EB_CHECK_ARG(n_cand >= 1 && cand_in && cand_out && state && partials && center_list,
                  "kcenters_step_rmsd: null pointer / n_cand < 1");
     EB_CHECK_ARG(n < (int64_t(1) << 40), "kcenters_step_rmsd: shard too large");
+    // TMA-staged kernel for large shards.  box = 12 rows x A_pad/P floats: the inner box
+    // dimension is limited to 256 elements and must be a multiple of 16 bytes, the row index
+    // (3 * frame) to int32; every part of a row must be whole 128-byte lines (aligned shared
+    // memory stages, no partial-line fetches: at 264 atoms, 528-byte half rows, the TMA kernel
+    // is slower than the LDG kernel).  Measured at 1.25M x 500 (ms per step): LDG kernel 1.26;
+    // ring (P,S) = (2,2) 1.11; (4,4) 1.22; (8,8) 1.56 -- big copies win, so P is the smallest
+    // split that respects the 256-element box limit and S = 2 fills shared memory.
+    const int A_pad_ = rmsd_apad(n_atoms);
+    constexpr int S = 2;
+    const int P = A_pad_ <= 256 ? 1 : (A_pad_ <= 512 ? 2 : 4);
+    const size_t tma_smem = step_tma_smem_bytes(A_pad_, P, S);
+    const bool use_tma = exact && k1_tma_enabled() && k1_variant() == 0 &&
+                         tma_smem <= 227 * 1024 && pick_rounds(n) == 8 && A_pad_ / P <= 256 &&
+                         A_pad_ % (32 * P) == 0 && 3 * n < (int64_t(1) << 31);
+    if (use_tma) {
+        CUtensorMap tmap;
+        const int trc = make_tmap_2d(&tmap, xyz_soa, CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                                     sizeof(float), (uint64_t)(3 * n), (uint64_t)A_pad_,
+                                     (uint64_t)A_pad_ * sizeof(float), 12,
+                                     (uint32_t)(A_pad_ / P), CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (trc != EB_OK) return trc;
+        auto kern = k_kcenters_step_rmsd_tma<2, S>;
+        if (P == 1) kern = k_kcenters_step_rmsd_tma<1, S>;
+        if (P == 4) kern = k_kcenters_step_rmsd_tma<4, S>;
+        EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)tma_smem));
+        const size_t rec_bytes = sizeof(RecHeader) + sizeof(float) * 3 * (size_t)A_pad_;
+        long chunks = (n + 31) / 32;
+        long blocks = (chunks + kStepWarps - 1) / kStepWarps;
+        if (blocks > sm_count()) blocks = sm_count();
+        for (int it = 0; it < n_steps; ++it) {
+            kern<<<(int)blocks, kStepThreads, tma_smem, (cudaStream_t)stream>>>(
+                xyz_soa, traces, n, n_atoms, A_pad_, frame_offset, (const unsigned char *)cand_in,
+                n_cand, rec_bytes, dist, assign, n_clusters_limit, dist_cutoff, state,
+                center_list, (Partial *)partials, (unsigned char *)cand_out, tmap);
+            EB_LAUNCH_CHECK();
+        }
+        return EB_OK;
+    }
     for (int it = 0; it < n_steps; ++it) {
         const int rc =
             exact ? launch_step<true, kModeStep>(xyz_soa, traces, n, n_atoms, frame_offset,

@@ -75,3 +75,21 @@ def test_c2_features_full_size(cuda):
     sel = r.assignments == k - 1
     np.testing.assert_array_equal(d_last[sel], r.distances[sel])
     assert np.all(d_last[~sel] >= r.distances[~sel])
+
+
+@pytest.mark.parametrize("A", [500, 256, 1000, 100, 264, 40])
+def test_tma_staged_step_equals_ldg_step(cuda, A, monkeypatch):
+    """Large shards run the TMA-staged step kernel when the padded row splits into whole
+    128-byte lines (500 -> 512: two parts, 256: one, 1000 -> 1024: four); other atom counts
+    (100, 264, 40) must fall back to the LDG kernel.  Either way the run equals the exact
+    many-centres kernel bit for bit (same summation order)."""
+    torch = cuda
+    from enspara_b200 import synth
+    from enspara_b200.cluster import _ops, kcenters, util
+    n = 80_000 if A <= 500 else 76_000          # >= 32 frames x resident warps: TMA eligible
+    X = synth.device_trajectory(n, A, seed=A)
+    r, eng = kcenters.kcenters(X, "rmsd", n_clusters=12, _return_engine=True)
+    c = [int(i) for i in r.center_indices]
+    cen = X.gather(torch.as_tensor(c, device="cuda"))
+    d2, a2 = _ops.assign_device(util.RMSD, X, cen)
+    assert torch.equal(a2, eng.assign) and torch.equal(d2, eng.dist)
