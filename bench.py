@@ -299,9 +299,9 @@ def run_b200(args):
     achieved = bytes_per_launch / mean_launch_s / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "kernel": ("k_kcenters_step_rmsd_tma<2,2>" if exact and os.environ.get(
-                    "EB_K1_TMA", "1") != "0" and A == 500 else
-                    "k_kcenters_step_rmsd<exact=%d>" % int(exact)),
+                "kernel": ("k_kcenters_step_rmsd_tma" if exact and
+                           eng.lib.eb_kcenters_step_rmsd_uses_tma(n_local, A) else
+                           "k_kcenters_step_rmsd<exact=%d>" % int(exact)),
                 "peak_note": "peak is the measured device COPY bandwidth (reads + writes); this "
                              "kernel only reads, and a read-only stream can exceed it (ncu: "
                              "84.9 % of the 8.18 TB/s DRAM peak)",

@@ -43,6 +43,7 @@ SIGNATURES = {
     "eb_gather_frames": (_int, [_vp, _vp, _int, _vp, _i64, _vp, _vp, _vp]),
     "eb_kcenters_step_rmsd": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _int, _vp, _vp, _i32,
                                      _dbl, _vp, _vp, _vp, _vp, _int, _int, _vp]),
+    "eb_kcenters_step_rmsd_uses_tma": (_int, [_i64, _int]),
     "eb_kcenters_step_rmsd_tri": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _int, _vp, _vp, _i32,
                                          _dbl, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64,
                                          _int, _vp]),

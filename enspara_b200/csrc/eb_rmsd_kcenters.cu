@@ -563,6 +563,23 @@ static size_t step_tma_smem_bytes(int A_pad, int P, int S)
            sizeof(double) * kStepWarps * 32 * kSumStride + sizeof(double) * 3 * (size_t)A_pad;
 }
 
+constexpr int kTmaRingStages = 2;
+static int tma_parts(int A_pad) { return A_pad <= 256 ? 1 : (A_pad <= 512 ? 2 : 4); }
+static int k1_tma_enabled();
+static int pick_rounds(long n);
+static int k1_variant();
+
+// whether the exact step of a shard of n frames runs the TMA-staged kernel (see the dispatch in
+// eb_kcenters_step_rmsd for the reasons behind each condition)
+static bool step_uses_tma(long n, int n_atoms)
+{
+    const int A_pad = rmsd_apad(n_atoms);
+    const int P = tma_parts(A_pad);
+    return k1_tma_enabled() && k1_variant() == 0 &&
+           step_tma_smem_bytes(A_pad, P, kTmaRingStages) <= 227 * 1024 && pick_rounds(n) == 8 &&
+           A_pad / P <= 256 && A_pad % (32 * P) == 0 && 3 * n < (int64_t(1) << 31);
+}
+
 // TMA-staged kernel for large shards (default); EB_K1_TMA=0 forces the LDG kernel (A/B switch)
 static int k1_tma_enabled()
 {
@@ -695,6 +712,7 @@ const char *eb_last_error(void) { return eb::g_err; }
 int eb_sm_count(void) { return eb::sm_count(); }
 
 int eb_rmsd_apad(int n_atoms) { return rmsd_apad(n_atoms); }
+int eb_kcenters_step_rmsd_uses_tma(int64_t n, int n_atoms) { return step_uses_tma(n, n_atoms); }
 size_t eb_rmsd_record_bytes(int n_atoms)
 {
     return sizeof(RecHeader) + sizeof(float) * 3 * (size_t)rmsd_apad(n_atoms);
@@ -772,12 +790,10 @@ int eb_kcenters_step_rmsd(const float *xyz_soa, const double *traces, int64_t n,
     // ring (P,S) = (2,2) 1.11; (4,4) 1.22; (8,8) 1.56 -- big copies win, so P is the smallest
     // split that respects the 256-element box limit and S = 2 fills shared memory.
     const int A_pad_ = rmsd_apad(n_atoms);
-    constexpr int S = 2;
-    const int P = A_pad_ <= 256 ? 1 : (A_pad_ <= 512 ? 2 : 4);
+    constexpr int S = kTmaRingStages;
+    const int P = tma_parts(A_pad_);
     const size_t tma_smem = step_tma_smem_bytes(A_pad_, P, S);
-    const bool use_tma = exact && k1_tma_enabled() && k1_variant() == 0 &&
-                         tma_smem <= 227 * 1024 && pick_rounds(n) == 8 && A_pad_ / P <= 256 &&
-                         A_pad_ % (32 * P) == 0 && 3 * n < (int64_t(1) << 31);
+    const bool use_tma = exact && step_uses_tma(n, n_atoms);
     if (use_tma) {
         CUtensorMap tmap;
         const int trc = make_tmap_2d(&tmap, xyz_soa, CU_TENSOR_MAP_DATA_TYPE_FLOAT32,

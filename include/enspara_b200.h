@@ -110,6 +110,9 @@ int eb_gather_frames(const float *xyz_soa, const double *traces, int n_atoms,
  * float64 (parity mode, default); exact=0 uses float32 blocks of 4 atoms + float64 block sums.
  * n_steps > 1 queues that many consecutive iterations in one call (single shard only: the
  * next step reads the record this one wrote; sharded runs interleave the all-gather). */
+/* 1 when the exact step of a shard of n frames runs the TMA-staged kernel
+ * (k_kcenters_step_rmsd_tma), 0 when it runs the LDG kernel; reporting aid for benchmarks. */
+int eb_kcenters_step_rmsd_uses_tma(int64_t n, int n_atoms);
 int eb_kcenters_step_rmsd(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
                           int64_t frame_offset, const void *cand_in, int n_cand,
                           float *dist, int32_t *assign, int32_t n_clusters_limit,
