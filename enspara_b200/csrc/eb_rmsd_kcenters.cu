@@ -365,20 +365,24 @@ k_kcenters_step_rmsd(const float *__restrict__ xyz, const double *__restrict__ t
 // ------------------------------------------------------------------------------------------
 // P: parts a coordinate row is cut into (a stage holds A_pad / P atoms of four frames);
 // S: ring depth (S - 1 stages are in flight while one is consumed).
-template <int P, int S>
+// MODE: kModeStep (the k-centers iteration) or kModeDistOnly (md.rmsd(X, y): the centre comes
+// from center_direct / center_trace_direct and out_only[f] receives the distance).
+template <int P, int S, int MODE = kModeStep>
 __global__ void __launch_bounds__(kStepThreads, 1)
 k_kcenters_step_rmsd_tma(const float *__restrict__ xyz, const double *__restrict__ traces, long n,
                          int A, int A_pad, long frame_offset, const unsigned char *cand_in,
                          int n_cand, size_t rec_bytes, float *dist, int *assign,
                          int n_clusters_limit, double cutoff, eb_kc_state *state,
                          int64_t *center_list, Partial *partials, unsigned char *cand_out,
-                         const __grid_constant__ CUtensorMap tmap)
+                         const __grid_constant__ CUtensorMap tmap,
+                         const float *center_direct = nullptr,
+                         const double *center_trace_direct = nullptr, float *out_only = nullptr)
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_tma[];
     constexpr int kStagesPerChunk = 8 * P;                       // 8 rounds x P parts
     const uint32_t part_row_bytes = 4u * (uint32_t)A_pad / P;    // one part of a coordinate row
     const uint32_t stage_bytes = 12u * part_row_bytes;           // 4 frames x 3 rows
-    unsigned char *ring = smem_raw;                              // [warps][S][stage_bytes]
+    unsigned char *ring = smem_tma;                              // [warps][S][stage_bytes]
     uint64_t *bars = reinterpret_cast<uint64_t *>(ring + (size_t)kStepWarps * S * stage_bytes);
     StepSmem *ss = reinterpret_cast<StepSmem *>(bars + kStepWarps * S);
     double *sums = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(ss) +
@@ -401,27 +405,33 @@ k_kcenters_step_rmsd_tma(const float *__restrict__ xyz, const double *__restrict
     // ---- prologue: winner among the gathered candidates, stop rule -------------------------
     int k = 0;
     CenterSmem cs = center_smem_carve(center_base, A4);
-    double cd;
-    int64_t ci;
-    const int r_win = pick_candidate(cand_in, n_cand, rec_bytes, cd, ci);
-    const bool active = (r_win >= 0) && step_active(state, n_clusters_limit, cd, cutoff, k);
-    if (!active) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            if (!state->done) {
-                state->done = 1;
-                state->maxdist = cd;
-            } else {
-                state->n_noop += 1;
+    double Gb;
+    if (MODE == kModeStep) {
+        double cd;
+        int64_t ci;
+        const int r_win = pick_candidate(cand_in, n_cand, rec_bytes, cd, ci);
+        const bool active = (r_win >= 0) && step_active(state, n_clusters_limit, cd, cutoff, k);
+        if (!active) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                if (!state->done) {
+                    state->done = 1;
+                    state->maxdist = cd;
+                } else {
+                    state->n_noop += 1;
+                }
             }
+            return;
         }
-        return;
-    }
-    const unsigned char *rec = cand_in + (size_t)r_win * rec_bytes;
-    const double Gb = __ldcg(&reinterpret_cast<const RecHeader *>(rec)->trace);
-    center_smem_fill(cs, reinterpret_cast<const float *>(rec + sizeof(RecHeader)), A_pad);
-    if (threadIdx.x == 0) {
-        ss->center_index = ci;
-        ss->maxdist = cd;
+        const unsigned char *rec = cand_in + (size_t)r_win * rec_bytes;
+        Gb = __ldcg(&reinterpret_cast<const RecHeader *>(rec)->trace);
+        center_smem_fill(cs, reinterpret_cast<const float *>(rec + sizeof(RecHeader)), A_pad);
+        if (threadIdx.x == 0) {
+            ss->center_index = ci;
+            ss->maxdist = cd;
+        }
+    } else {
+        Gb = __ldg(center_trace_direct);
+        center_smem_fill(cs, center_direct, A_pad);
     }
     __syncthreads();
 
@@ -517,19 +527,24 @@ k_kcenters_step_rmsd_tma(const float *__restrict__ xyz, const double *__restrict
 #pragma unroll
             for (int e = 0; e < 9; ++e) mm[e] = src[e];
             const float d = rmsd_from_msd(qcp_msd(mm, traces[f], Gb, A));
-            const float old = dist[f];
-            if (d < old) {  // strict '<', kcenters.py:304
-                dist[f] = d;
-                assign[f] = k;
-            }
-            const double cur = (double)((d < old) ? d : old);
-            if (cur > best_d) {
-                best_d = cur;
-                best_i = f;
+            if (MODE == kModeDistOnly) {
+                out_only[f] = d;
+            } else {
+                const float old = dist[f];
+                if (d < old) {  // strict '<', kcenters.py:304
+                    dist[f] = d;
+                    assign[f] = k;
+                }
+                const double cur = (double)((d < old) ? d : old);
+                if (cur > best_d) {
+                    best_d = cur;
+                    best_i = f;
+                }
             }
         }
         __syncwarp();
     }
+    if (MODE == kModeDistOnly) return;
 
     // ---- epilogue: shard arg-max, candidate record, centre list ----------------------------
     if (!grid_argmax_last_block(best_d, best_i, partials, state, ss->red, &ss->flag)) return;
@@ -814,7 +829,8 @@ int eb_kcenters_step_rmsd(const float *xyz_soa, const double *traces, int64_t n,
             kern<<<(int)blocks, kStepThreads, tma_smem, (cudaStream_t)stream>>>(
                 xyz_soa, traces, n, n_atoms, A_pad_, frame_offset, (const unsigned char *)cand_in,
                 n_cand, rec_bytes, dist, assign, n_clusters_limit, dist_cutoff, state,
-                center_list, (Partial *)partials, (unsigned char *)cand_out, tmap);
+                center_list, (Partial *)partials, (unsigned char *)cand_out, tmap, nullptr,
+                nullptr, nullptr);
             EB_LAUNCH_CHECK();
         }
         return EB_OK;
@@ -900,6 +916,30 @@ int eb_rmsd_one_to_all(const float *xyz_soa, const double *traces, int64_t n, in
     if (n == 0) return EB_OK;
     EB_CHECK_ARG(xyz_soa && traces && center_soa && center_trace && out,
                  "rmsd_one_to_all: null pointer");
+    if (exact && step_uses_tma(n, n_atoms)) {
+        const int A_pad = rmsd_apad(n_atoms);
+        constexpr int S = kTmaRingStages;
+        const int P = tma_parts(A_pad);
+        const size_t tma_smem = step_tma_smem_bytes(A_pad, P, S);
+        CUtensorMap tmap;
+        const int trc = make_tmap_2d(&tmap, xyz_soa, CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                                     sizeof(float), (uint64_t)(3 * n), (uint64_t)A_pad,
+                                     (uint64_t)A_pad * sizeof(float), 12, (uint32_t)(A_pad / P),
+                                     CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (trc != EB_OK) return trc;
+        auto kern = k_kcenters_step_rmsd_tma<2, S, kModeDistOnly>;
+        if (P == 1) kern = k_kcenters_step_rmsd_tma<1, S, kModeDistOnly>;
+        if (P == 4) kern = k_kcenters_step_rmsd_tma<4, S, kModeDistOnly>;
+        EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)tma_smem));
+        long blocks = ((n + 31) / 32 + kStepWarps - 1) / kStepWarps;
+        if (blocks > sm_count()) blocks = sm_count();
+        kern<<<(int)blocks, kStepThreads, tma_smem, (cudaStream_t)stream>>>(
+            xyz_soa, traces, n, n_atoms, A_pad, 0, nullptr, 0, 0, nullptr, nullptr, 0, 0.0,
+            nullptr, nullptr, nullptr, nullptr, tmap, center_soa, center_trace, out);
+        EB_LAUNCH_CHECK();
+        return EB_OK;
+    }
     if (exact)
         return launch_step<true, kModeDistOnly>(xyz_soa, traces, n, n_atoms, 0, nullptr, 0,
                                                 nullptr, nullptr, 0, 0.0, nullptr, nullptr,

@@ -93,3 +93,8 @@ def test_tma_staged_step_equals_ldg_step(cuda, A, monkeypatch):
     cen = X.gather(torch.as_tensor(c, device="cuda"))
     d2, a2 = _ops.assign_device(util.RMSD, X, cen)
     assert torch.equal(a2, eng.assign) and torch.equal(d2, eng.dist)
+    # md.rmsd(X, centre) for the last centre (TMA-staged distance-only kernel when eligible)
+    # agrees with the k-centers state wherever that centre won, and bounds it elsewhere
+    d1 = _ops.one_to_all_device(util.RMSD, X, X.gather(torch.as_tensor(c[-1:], device="cuda")))
+    won = eng.assign == len(c) - 1
+    assert torch.equal(d1[won], eng.dist[won]) and bool((d1[~won] >= eng.dist[~won]).all())
