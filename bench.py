@@ -282,6 +282,9 @@ def run_b200(args):
     per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
     st = eng.read_state()
     assert st.n_centers == K + W, "steps were skipped: %d != %d" % (st.n_centers, K + W)
+    exchange = ("none (single GPU)" if world == 1 else
+                "peer-memory stores + flags fused into the step kernel (no collective launch)"
+                if eng.p2p else "one NCCL all-gather of candidate records per step")
     clk = clocks.stop(t0, t1) if rank == 0 else None
 
     tmax = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
@@ -376,8 +379,8 @@ def run_b200(args):
             "config": {"workload": WORKLOAD, "frames_per_gpu": n_local, "n_atoms": A,
                        "frames_total": n_total, "l2": "inputs (%.1f GB per GPU) larger than L2; "
                        "no flush needed" % (n_local * A * 12 / 1e9),
-                       "parallelism": "frames sharded contiguously, 1 all-gather of candidate "
-                                      "records per step" if world > 1 else "single GPU"},
+                       "parallelism": "frames sharded contiguously; candidate exchange: "
+                                      + exchange if world > 1 else "single GPU"},
             "roofline": roofline, "clocks": clk, "gpu_launches": K,
             "e2e": e2e, "cpu_baseline": cpu,
         }

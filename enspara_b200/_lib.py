@@ -44,6 +44,11 @@ SIGNATURES = {
     "eb_kcenters_step_rmsd": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _int, _vp, _vp, _i32,
                                      _dbl, _vp, _vp, _vp, _vp, _int, _int, _vp]),
     "eb_kcenters_step_rmsd_uses_tma": (_int, [_i64, _int]),
+    "eb_exch_bytes": (_sz, [_int, _int]),
+    "eb_kcenters_seed_rmsd_p2p": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _int, _int, _vp, _i32,
+                                         _vp, _vp, _vp, _vp]),
+    "eb_kcenters_step_rmsd_p2p": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _int, _int, _vp, _vp,
+                                         _i32, _dbl, _vp, _vp, _vp, _vp, _int, _int, _vp]),
     "eb_kcenters_step_rmsd_tri": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _int, _vp, _vp, _i32,
                                          _dbl, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64,
                                          _int, _vp]),

@@ -76,6 +76,45 @@ class KCentersEngine:
         self.triangle = bool(triangle) and self.is_rmsd and self.exact
         self.center_store = self.center_store_traces = self.cc = None
         self._queued = 0            # host upper bound of the number of centres
+        # sharded RMSD runs exchange the candidate records through peer memory inside the step
+        # kernel (no collective launch); anything else uses one NCCL all-gather per step
+        self.p2p = self._setup_p2p()
+
+    # -- fused peer-memory exchange --------------------------------------------------------
+    def _setup_p2p(self):
+        """Symmetric exchange buffers (torch symmetric memory: CUDA VMM + peer mapping) for the
+        fused step + exchange kernels.  Every rank must take the same path, so the decision is
+        agreed on with one collective; any failure falls back to the NCCL all-gather."""
+        import logging
+        import os
+        sh = self.shard
+        if sh.size <= 1:
+            return False
+        want = (self.is_rmsd and not self.triangle and sh.size <= 8
+                and os.environ.get("ENSPARA_B200_P2P", "1") != "0")
+        ok, err = False, None
+        if want:
+            try:
+                import torch.distributed as dist
+                import torch.distributed._symmetric_memory as symm
+                nbytes = int(self.lib.eb_exch_bytes(self.data.n_atoms, sh.size))
+                buf = symm.empty(nbytes, dtype=torch.uint8, device=self.dev)
+                hdl = symm.rendezvous(buf, dist.group.WORLD)
+                buf.zero_()
+                self._exch_buf, self._exch_hdl = buf, hdl
+                self._exch_peers = torch.tensor([int(p) for p in hdl.buffer_ptrs],
+                                                dtype=torch.int64, device=self.dev)
+                ok = True
+            except Exception as exc:  # no peer access, old torch, ...
+                err = exc
+        all_ok = all(self.comm.all_gather_object(bool(ok)))
+        if want and not all_ok and sh.rank == 0:
+            logging.getLogger(__name__).warning(
+                "peer-memory candidate exchange unavailable (%r); using the NCCL all-gather", err)
+        if all_ok:
+            torch.cuda.synchronize()
+            self.comm.barrier()      # every buffer is zeroed before anyone publishes into it
+        return bool(all_ok)
 
     # -- state ---------------------------------------------------------------------------
     def set_state(self, distances, assignments):
@@ -97,6 +136,14 @@ class KCentersEngine:
 
     def seed(self, first_center_id=0):
         s = stream_ptr()
+        if self.p2p:
+            d = self.data
+            _lib.call("eb_kcenters_seed_rmsd_p2p", ptr(d.xyz), ptr(d.traces), self.n, d.n_atoms,
+                      self.shard.offset, ptr(self._exch_peers), self.shard.size,
+                      self.shard.rank, ptr(self.dist), int(first_center_id), ptr(self.state),
+                      ptr(self.partials), ptr(self.cand_out), s)
+            self.launches += 1
+            return
         if self.is_rmsd:
             d = self.data
             _lib.call("eb_kcenters_seed_rmsd", ptr(d.xyz), ptr(d.traces), self.n, d.n_atoms,
@@ -113,6 +160,16 @@ class KCentersEngine:
     def step(self, n_clusters_limit, cutoff, n_steps=1):
         """Queue ``n_steps`` iterations.  A single shard queues them inside one C call (no
         Python per launch); sharded runs interleave the candidate all-gather."""
+        if self.p2p:
+            d = self.data
+            _lib.call("eb_kcenters_step_rmsd_p2p", ptr(d.xyz), ptr(d.traces), self.n, d.n_atoms,
+                      self.shard.offset, ptr(self._exch_peers), self.shard.size,
+                      self.shard.rank, ptr(self.dist), ptr(self.assign), n_clusters_limit,
+                      float(cutoff), ptr(self.state), ptr(self.center_list), ptr(self.partials),
+                      ptr(self.cand_out), int(self.exact), int(n_steps), stream_ptr())
+            self.launches += n_steps
+            self._queued += n_steps
+            return
         if self.shard.size > 1 and n_steps > 1:
             for _ in range(n_steps):
                 self.step(n_clusters_limit, cutoff, 1)

@@ -140,6 +140,90 @@ __device__ __forceinline__ void block_argmax(double &d, int64_t &i, Partial *sh)
     __syncthreads();
 }
 
+// ------------------------------------------------------------------------------------------
+// Candidate exchange over peer memory (NVLink P2P), fused into the step kernel.
+//
+// The reference exchanges the new centre with two allgathers + a Bcast + a Barrier + an
+// allreduce per iteration (cluster/kcenters.py:332-348, mpi/ops.py:137-138).  Here every rank
+// owns one symmetric buffer (same layout on every GPU, mapped into every peer):
+//     [  0) u64 seq                  number of records this rank has published so far
+//     [128) u64 flags[2][8]          flags[p][r] = seq of the last record rank r put in parity p
+//     [256) records[2][size][stride] candidate records, double buffered by seq parity
+// The last block of a step writes its shard's candidate record straight into slot `rank` of
+// EVERY peer's buffer (plain stores over NVLink), fences at system scope and then releases
+// flags[p][rank] = seq on every peer.  The next step's prologue acquires the `size` flags of
+// its own buffer and reads the records locally: no collective launch, no host involvement.
+// Double buffering is enough: a rank can be at most one publish ahead of any peer, because
+// publishing record q+1 requires having consumed every peer's record q.
+// ------------------------------------------------------------------------------------------
+struct Exch {
+    const long long *peers;   // device array: base address of every rank's buffer (nullptr: off)
+    int size;
+    int rank;
+    unsigned rec_stride;      // bytes between records (>= record bytes, multiple of 16)
+};
+constexpr int kExchMaxRanks = 8;
+constexpr int kExchFlagsOff = 128;
+constexpr int kExchRecordsOff = 256;
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Consumer side (all threads of the block): wait until every rank's record of the current
+// sequence number has arrived in THIS rank's buffer; returns the local record array.
+__device__ __forceinline__ const unsigned char *exch_wait(const Exch &e)
+{
+    unsigned char *me = reinterpret_cast<unsigned char *>(e.peers[e.rank]);
+    const unsigned long long q = *reinterpret_cast<volatile unsigned long long *>(me);
+    const int p = (int)(q & 1ull);
+    if ((int)threadIdx.x < e.size) {
+        const unsigned long long *flag =
+            reinterpret_cast<const unsigned long long *>(me + kExchFlagsOff) +
+            p * kExchMaxRanks + threadIdx.x;
+        while (ld_acquire_sys(flag) != q) {
+        }
+    }
+    __syncthreads();
+    return me + kExchRecordsOff + (size_t)p * e.size * e.rec_stride;
+}
+
+// Publisher side (all threads of ONE block): `rec` (rec_bytes, a multiple of 16, in local global
+// memory, written by this block) goes to slot `rank` of every peer, then the flags are released.
+__device__ __forceinline__ void exch_publish(const Exch &e, const unsigned char *rec,
+                                             size_t rec_bytes)
+{
+    unsigned char *me = reinterpret_cast<unsigned char *>(e.peers[e.rank]);
+    const unsigned long long q = *reinterpret_cast<volatile unsigned long long *>(me) + 1ull;
+    const int p = (int)(q & 1ull);
+    __syncthreads();   // the record is complete
+    const int n4 = (int)(rec_bytes >> 4);
+    const float4 *src = reinterpret_cast<const float4 *>(rec);
+    for (int d = 0; d < e.size; ++d) {
+        float4 *dst = reinterpret_cast<float4 *>(
+            reinterpret_cast<unsigned char *>(e.peers[d]) + kExchRecordsOff +
+            ((size_t)p * e.size + e.rank) * e.rec_stride);
+        for (int t = threadIdx.x; t < n4; t += blockDim.x) dst[t] = __ldcg(src + t);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long *>(me) = q;
+    if ((int)threadIdx.x < e.size) {
+        unsigned long long *flag =
+            reinterpret_cast<unsigned long long *>(
+                reinterpret_cast<unsigned char *>(e.peers[threadIdx.x]) + kExchFlagsOff) +
+            p * kExchMaxRanks + e.rank;
+        st_release_sys(flag, q);
+    }
+}
+
 // Prologue shared by all step kernels: choose the winning candidate record.
 // Every thread gets the same answer.  Records with index < 0 are empty shards.
 __device__ __forceinline__ int pick_candidate(const unsigned char *cand, int n_cand,

@@ -154,7 +154,7 @@ k_kcenters_step_rmsd(const float *__restrict__ xyz, const double *__restrict__ t
                      int n_clusters_limit, double cutoff, eb_kc_state *state,
                      int64_t *center_list, Partial *partials, unsigned char *cand_out,
                      const float *center_direct, const double *center_trace_direct, float *out_only,
-                     float *cstore, double *cstore_traces, const float *__restrict__ cc)
+                     float *cstore, double *cstore_traces, const float *__restrict__ cc, Exch exch)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StepSmem *ss = reinterpret_cast<StepSmem *>(smem_raw);
@@ -169,8 +169,20 @@ k_kcenters_step_rmsd(const float *__restrict__ xyz, const double *__restrict__ t
     double Gb = 0.0;
     CenterSmem cs = center_smem_carve(center_base, A4);
 
+    const size_t rec_len = rec_bytes;   // bytes of one record (rec_bytes becomes the stride)
     if (MODE == kModeStep || MODE == kModeCC) {
         // ---- prologue: winner among the gathered candidates, stop rule -------------------
+        if (exch.peers) {
+            // peer-memory exchange: the records arrive in this rank's symmetric buffer; a run
+            // that already stopped publishes nothing, so do not wait for anything either
+            if (*reinterpret_cast<const volatile int32_t *>(&state->done)) {
+                if (MODE == kModeStep && blockIdx.x == 0 && threadIdx.x == 0) state->n_noop += 1;
+                return;
+            }
+            cand_in = exch_wait(exch);
+            n_cand = exch.size;
+            rec_bytes = exch.rec_stride;
+        }
         double cd;
         int64_t ci;
         const int r = pick_candidate(cand_in, n_cand, rec_bytes, cd, ci);
@@ -347,6 +359,7 @@ k_kcenters_step_rmsd(const float *__restrict__ xyz, const double *__restrict__ t
         state->blocks_done = 0;
         __threadfence();
     }
+    if (exch.peers) exch_publish(exch, cand_out, rec_len);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -374,9 +387,8 @@ k_kcenters_step_rmsd_tma(const float *__restrict__ xyz, const double *__restrict
                          int n_cand, size_t rec_bytes, float *dist, int *assign,
                          int n_clusters_limit, double cutoff, eb_kc_state *state,
                          int64_t *center_list, Partial *partials, unsigned char *cand_out,
-                         const __grid_constant__ CUtensorMap tmap,
-                         const float *center_direct = nullptr,
-                         const double *center_trace_direct = nullptr, float *out_only = nullptr)
+                         const __grid_constant__ CUtensorMap tmap, const float *center_direct,
+                         const double *center_trace_direct, float *out_only, Exch exch)
 {
     extern __shared__ __align__(128) unsigned char smem_tma[];
     constexpr int kStagesPerChunk = 8 * P;                       // 8 rounds x P parts
@@ -406,7 +418,17 @@ k_kcenters_step_rmsd_tma(const float *__restrict__ xyz, const double *__restrict
     int k = 0;
     CenterSmem cs = center_smem_carve(center_base, A4);
     double Gb;
+    const size_t rec_len = rec_bytes;   // bytes of one record (rec_bytes becomes the stride)
     if (MODE == kModeStep) {
+        if (exch.peers) {
+            if (*reinterpret_cast<const volatile int32_t *>(&state->done)) {
+                if (blockIdx.x == 0 && threadIdx.x == 0) state->n_noop += 1;
+                return;
+            }
+            cand_in = exch_wait(exch);
+            n_cand = exch.size;
+            rec_bytes = exch.rec_stride;
+        }
         double cd;
         int64_t ci;
         const int r_win = pick_candidate(cand_in, n_cand, rec_bytes, cd, ci);
@@ -569,6 +591,7 @@ k_kcenters_step_rmsd_tma(const float *__restrict__ xyz, const double *__restrict
         state->blocks_done = 0;
         __threadfence();
     }
+    if (exch.peers) exch_publish(exch, cand_out, rec_len);
 }
 
 static size_t step_tma_smem_bytes(int A_pad, int P, int S)
@@ -649,6 +672,7 @@ struct StepExtra {
     double *cstore_traces = nullptr;
     float *cc = nullptr;
     long grid_frames = -1;   // size the grid for this many frames instead of n (kModeCC)
+    Exch exch = {nullptr, 0, 0, 0};
 };
 
 template <bool EXACT, int MODE, int VAR, int ROUNDS>
@@ -677,7 +701,7 @@ static int launch_step_r(const float *xyz, const double *traces, long n, int A, 
         xyz, traces, n, A, A_pad, frame_offset, (const unsigned char *)cand_in, n_cand, rec_bytes,
         dist, assign, n_clusters_limit, cutoff, state, center_list, (Partial *)partials,
         (unsigned char *)cand_out, center_direct, center_trace_direct, out_only, ex.cstore,
-        ex.cstore_traces, ex.cc);
+        ex.cstore_traces, ex.cc, ex.exch);
     EB_LAUNCH_CHECK();
     return EB_OK;
 }
@@ -784,19 +808,14 @@ int eb_gather_frames(const float *xyz_soa, const double *traces, int n_atoms, co
     return EB_OK;
 }
 
-int eb_kcenters_step_rmsd(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
+// shared implementation of the step entry points: `exch.peers != nullptr` selects the fused
+// peer-memory candidate exchange (cand_in / n_cand are then ignored)
+static int step_rmsd_impl(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
                           int64_t frame_offset, const void *cand_in, int n_cand, float *dist,
                           int32_t *assign, int32_t n_clusters_limit, double dist_cutoff,
                           eb_kc_state *state, int64_t *center_list, void *partials,
-                          void *cand_out, int exact, int n_steps, void *stream)
+                          void *cand_out, int exact, int n_steps, Exch exch, void *stream)
 {
-    EB_CHECK_ARG(n >= 0 && n_atoms > 0, "kcenters_step_rmsd: bad shape");
-    EB_CHECK_ARG(n_steps >= 1, "kcenters_step_rmsd: n_steps < 1");
-    EB_CHECK_ARG(n_steps == 1 || (n_cand == 1 && cand_in == cand_out),
-                 "kcenters_step_rmsd: n_steps > 1 needs a single shard (cand_in == cand_out)");
-    EB_CHECK_ARG(n_cand >= 1 && cand_in && cand_out && state && partials && center_list,
-                 "kcenters_step_rmsd: null pointer / n_cand < 1");
-    EB_CHECK_ARG(n < (int64_t(1) << 40), "kcenters_step_rmsd: shard too large");
     // TMA-staged kernel for large shards.  box = 12 rows x A_pad/P floats: the inner box
     // dimension is limited to 256 elements and must be a multiple of 16 bytes, the row index
     // (3 * frame) to int32; every part of a row must be whole 128-byte lines (aligned shared
@@ -830,26 +849,111 @@ int eb_kcenters_step_rmsd(const float *xyz_soa, const double *traces, int64_t n,
                 xyz_soa, traces, n, n_atoms, A_pad_, frame_offset, (const unsigned char *)cand_in,
                 n_cand, rec_bytes, dist, assign, n_clusters_limit, dist_cutoff, state,
                 center_list, (Partial *)partials, (unsigned char *)cand_out, tmap, nullptr,
-                nullptr, nullptr);
+                nullptr, nullptr, exch);
             EB_LAUNCH_CHECK();
         }
         return EB_OK;
     }
+    StepExtra ex;
+    ex.exch = exch;
     for (int it = 0; it < n_steps; ++it) {
-        const int rc =
-            exact ? launch_step<true, kModeStep>(xyz_soa, traces, n, n_atoms, frame_offset,
-                                                 cand_in, n_cand, dist, assign, n_clusters_limit,
-                                                 dist_cutoff, state, center_list, partials,
-                                                 cand_out, nullptr, nullptr, nullptr,
-                                                 (cudaStream_t)stream)
-                  : launch_step<false, kModeStep>(xyz_soa, traces, n, n_atoms, frame_offset,
-                                                  cand_in, n_cand, dist, assign, n_clusters_limit,
-                                                  dist_cutoff, state, center_list, partials,
-                                                  cand_out, nullptr, nullptr, nullptr,
-                                                  (cudaStream_t)stream);
+        int rc;
+        if (exact && k1_variant() == 0)
+            rc = launch_step_v<true, kModeStep, 0>(xyz_soa, traces, n, n_atoms, frame_offset,
+                                                   cand_in, n_cand, dist, assign,
+                                                   n_clusters_limit, dist_cutoff, state,
+                                                   center_list, partials, cand_out, nullptr,
+                                                   nullptr, nullptr, (cudaStream_t)stream, ex);
+        else if (exact)
+            rc = launch_step<true, kModeStep>(xyz_soa, traces, n, n_atoms, frame_offset, cand_in,
+                                              n_cand, dist, assign, n_clusters_limit, dist_cutoff,
+                                              state, center_list, partials, cand_out, nullptr,
+                                              nullptr, nullptr, (cudaStream_t)stream);
+        else
+            rc = launch_step_v<false, kModeStep, 0>(xyz_soa, traces, n, n_atoms, frame_offset,
+                                                    cand_in, n_cand, dist, assign,
+                                                    n_clusters_limit, dist_cutoff, state,
+                                                    center_list, partials, cand_out, nullptr,
+                                                    nullptr, nullptr, (cudaStream_t)stream, ex);
         if (rc != EB_OK) return rc;
     }
     return EB_OK;
+}
+
+int eb_kcenters_step_rmsd(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
+                          int64_t frame_offset, const void *cand_in, int n_cand, float *dist,
+                          int32_t *assign, int32_t n_clusters_limit, double dist_cutoff,
+                          eb_kc_state *state, int64_t *center_list, void *partials,
+                          void *cand_out, int exact, int n_steps, void *stream)
+{
+    EB_CHECK_ARG(n >= 0 && n_atoms > 0, "kcenters_step_rmsd: bad shape");
+    EB_CHECK_ARG(n_steps >= 1, "kcenters_step_rmsd: n_steps < 1");
+    EB_CHECK_ARG(n_steps == 1 || (n_cand == 1 && cand_in == cand_out),
+                 "kcenters_step_rmsd: n_steps > 1 needs a single shard (cand_in == cand_out)");
+    EB_CHECK_ARG(n_cand >= 1 && cand_in && cand_out && state && partials && center_list,
+                 "kcenters_step_rmsd: null pointer / n_cand < 1");
+    EB_CHECK_ARG(n < (int64_t(1) << 40), "kcenters_step_rmsd: shard too large");
+    const Exch off = {nullptr, 0, 0, 0};
+    return step_rmsd_impl(xyz_soa, traces, n, n_atoms, frame_offset, cand_in, n_cand, dist, assign,
+                          n_clusters_limit, dist_cutoff, state, center_list, partials, cand_out,
+                          exact, n_steps, off, stream);
+}
+
+// ---- fused peer-memory candidate exchange (see eb_common.cuh: struct Exch) ------------------
+size_t eb_exch_bytes(int n_atoms, int n_ranks)
+{
+    const size_t rec = sizeof(RecHeader) + sizeof(float) * 3 * (size_t)rmsd_apad(n_atoms);
+    const size_t stride = (rec + 127) & ~size_t(127);
+    return kExchRecordsOff + 2 * (size_t)n_ranks * stride;
+}
+
+static int make_exch(Exch *e, const void *peers_dev, int n_ranks, int rank, int n_atoms)
+{
+    EB_CHECK_ARG(peers_dev && n_ranks >= 1 && n_ranks <= kExchMaxRanks && rank >= 0 &&
+                     rank < n_ranks,
+                 "p2p exchange: need 1..8 ranks and the device array of peer buffers");
+    const size_t rec = sizeof(RecHeader) + sizeof(float) * 3 * (size_t)rmsd_apad(n_atoms);
+    e->peers = (const long long *)peers_dev;
+    e->size = n_ranks;
+    e->rank = rank;
+    e->rec_stride = (unsigned)((rec + 127) & ~size_t(127));
+    return EB_OK;
+}
+
+int eb_kcenters_step_rmsd_p2p(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
+                              int64_t frame_offset, const void *peers_dev, int n_ranks, int rank,
+                              float *dist, int32_t *assign, int32_t n_clusters_limit,
+                              double dist_cutoff, eb_kc_state *state, int64_t *center_list,
+                              void *partials, void *cand_out, int exact, int n_steps,
+                              void *stream)
+{
+    EB_CHECK_ARG(n >= 0 && n_atoms > 0 && n_steps >= 1, "kcenters_step_rmsd_p2p: bad shape");
+    EB_CHECK_ARG(cand_out && state && partials && center_list && (n == 0 || (dist && assign)),
+                 "kcenters_step_rmsd_p2p: null pointer");   // an empty shard has no dist / assign
+    Exch e;
+    const int rc = make_exch(&e, peers_dev, n_ranks, rank, n_atoms);
+    if (rc != EB_OK) return rc;
+    return step_rmsd_impl(xyz_soa, traces, n, n_atoms, frame_offset, nullptr, 0, dist, assign,
+                          n_clusters_limit, dist_cutoff, state, center_list, partials, cand_out,
+                          exact, n_steps, e, stream);
+}
+
+int eb_kcenters_seed_rmsd_p2p(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
+                              int64_t frame_offset, const void *peers_dev, int n_ranks, int rank,
+                              const float *dist, int32_t first_center_id, eb_kc_state *state,
+                              void *partials, void *cand_out, void *stream)
+{
+    EB_CHECK_ARG(n >= 0 && n_atoms > 0, "kcenters_seed_rmsd_p2p: bad shape");
+    EB_CHECK_ARG(state && partials && cand_out, "kcenters_seed_rmsd_p2p: null pointer");
+    StepExtra ex;
+    const int rc = make_exch(&ex.exch, peers_dev, n_ranks, rank, n_atoms);
+    if (rc != EB_OK) return rc;
+    EB_CUDA(cudaMemsetAsync(state, 0, sizeof(eb_kc_state), (cudaStream_t)stream));
+    return launch_step_v<true, kModeSeed, 0>(xyz_soa, traces, n, n_atoms, frame_offset, nullptr,
+                                             0, const_cast<float *>(dist), nullptr,
+                                             first_center_id, 0.0, state, nullptr, partials,
+                                             cand_out, nullptr, nullptr, nullptr,
+                                             (cudaStream_t)stream, ex);
 }
 
 // Triangle-inequality variant (kcenters.py:287-296, `use_triangle_inequality=True`): per
@@ -936,7 +1040,8 @@ int eb_rmsd_one_to_all(const float *xyz_soa, const double *traces, int64_t n, in
         if (blocks > sm_count()) blocks = sm_count();
         kern<<<(int)blocks, kStepThreads, tma_smem, (cudaStream_t)stream>>>(
             xyz_soa, traces, n, n_atoms, A_pad, 0, nullptr, 0, 0, nullptr, nullptr, 0, 0.0,
-            nullptr, nullptr, nullptr, nullptr, tmap, center_soa, center_trace, out);
+            nullptr, nullptr, nullptr, nullptr, tmap, center_soa, center_trace, out,
+            Exch{nullptr, 0, 0, 0});
         EB_LAUNCH_CHECK();
         return EB_OK;
     }

@@ -121,6 +121,25 @@ int eb_kcenters_step_rmsd(const float *xyz_soa, const double *traces, int64_t n,
 /* seed: arg-max of the CURRENT dist array -> cand_out (all +inf gives frame 0, which is the
  * reference's first centre, kcenters.py:199,282,326-328); resets *state with
  * n_centers = first_center_id (> 0 when continuing from init_centers, kcenters.py:200-206). */
+/* Fused step + candidate exchange over peer memory (NVLink P2P).  Replaces, per iteration, the
+ * reference's two allgathers + Bcast + Barrier + allreduce (cluster/kcenters.py:332-348,
+ * mpi/ops.py:137-138) WITHOUT any collective launch: the last block of a step stores its shard's
+ * candidate record into every peer's symmetric buffer and releases a per-rank flag; the next
+ * step's prologue acquires the flags of its own buffer.  peers_dev: device array of n_ranks
+ * int64 base addresses of the ranks' exchange buffers (eb_exch_bytes(n_atoms, n_ranks) bytes
+ * each, zero-initialised, mapped into every peer -- e.g. torch symmetric memory); every rank
+ * must queue the same sequence of seed / step launches.  n_steps > 1 is allowed. */
+size_t eb_exch_bytes(int n_atoms, int n_ranks);
+int eb_kcenters_seed_rmsd_p2p(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
+                              int64_t frame_offset, const void *peers_dev, int n_ranks, int rank,
+                              const float *dist, int32_t first_center_id, eb_kc_state *state,
+                              void *partials, void *cand_out, void *stream);
+int eb_kcenters_step_rmsd_p2p(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
+                              int64_t frame_offset, const void *peers_dev, int n_ranks, int rank,
+                              float *dist, int32_t *assign, int32_t n_clusters_limit,
+                              double dist_cutoff, eb_kc_state *state, int64_t *center_list,
+                              void *partials, void *cand_out, int exact, int n_steps,
+                              void *stream);
 /* Triangle-inequality variant of the step (cluster/kcenters.py:287-296,
  * use_triangle_inequality=True).  center_store (store_capacity x 3*A_pad floats) and
  * center_store_traces hold the coordinates of the centres chosen so far (slots

@@ -18,7 +18,8 @@ def main():
     rank, size = mpi.rank(), mpi.size()
     ok = True
     for (n, A, kw) in ((3001, 50, dict(n_clusters=25)), (2000, 264, dict(dist_cutoff=1.9)),
-                       (5, 10, dict(n_clusters=4))):
+                       (5, 10, dict(n_clusters=4)), (1, 10, dict(n_clusters=1)),
+                       (3, 10, dict(n_clusters=3))):      # the last two leave shards EMPTY
         X = synth.trajectory(n, A, seed=7)
         bounds = np.linspace(0, n, size + 1).astype(int)
         mine = X[bounds[rank]:bounds[rank + 1]]
