@@ -116,3 +116,21 @@ def test_reassign_streams_files_and_matches_oracle(tmp_path, frame0_xyz, monkeyp
     with pytest.raises(ImproperlyConfigured):          # batch smaller than the largest file
         monkeypatch.setattr(rz, "determine_batch_size", lambda *a, **k: (100, 0.0))
         rz.batch_reassign([(f, None, None) for f in files], centers, lengths, 0.5)
+
+
+def test_determine_batch_size_bounds(monkeypatch):
+    """Two pinned staging buffers + the device copy bound a batch; the cap never cuts below the
+    largest file while that still fits the hard (RAM / HBM) bound."""
+    import types
+    import psutil
+    monkeypatch.setattr(psutil, "virtual_memory",
+                        lambda: types.SimpleNamespace(total=64 << 30))
+    bpf = 500 * 3 * 4
+    hard = int((64 << 30) * 0.5 / 2 / bpf)              # no CUDA here: RAM bound only
+    n, gb = rz.determine_batch_size(500, 4, 0.5)
+    assert n == min(hard, rz.BATCH_BYTES_CAP // bpf) and abs(gb - n * bpf / 2 ** 30) < 1e-9
+    big = rz.BATCH_BYTES_CAP // bpf + 1000              # a file larger than the soft cap
+    n2, _ = rz.determine_batch_size(500, 4, 0.5, largest_file=big)
+    assert n2 == big
+    n3, _ = rz.determine_batch_size(500, 4, 0.5, largest_file=10 * hard)
+    assert n3 == hard                                   # ... but never beyond the hard bound
