@@ -1,10 +1,21 @@
-"""``timed`` context manager (reference: enspara/util/log.py:5-10)."""
+"""Wall-clock logging helper used by the apps (the reference has a context manager of the same
+name and call convention, enspara/util/log.py)."""
 import time
-from contextlib import contextmanager
 
 
-@contextmanager
-def timed(fmt, log_func):
-    t0 = time.perf_counter()
-    yield
-    log_func(fmt % (time.perf_counter() - t0))
+class timed:
+    """``with timed("Wrote centers in %.2f sec.", logger.info): ...`` logs the elapsed seconds
+    when the block finishes normally; the measurement stays available as ``.seconds``."""
+
+    def __init__(self, fmt, log_func):
+        self.fmt, self.log_func, self.seconds = fmt, log_func, None
+
+    def __enter__(self):
+        self._start = time.perf_counter()
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        self.seconds = time.perf_counter() - self._start
+        if exc_type is None:
+            self.log_func(self.fmt % self.seconds)
+        return False
