@@ -133,3 +133,15 @@ def test_synth_is_counter_based():
     f = synth.features(50, 8, seed=1)
     assert_array_equal(f[20:30], synth.features(10, 8, seed=1, first_row=20))
     assert f.min() >= 0 and f.max() < 1
+
+
+def test_timed_logs_elapsed_seconds():
+    from enspara_b200.util.log import timed
+    seen = []
+    with timed("took %.3f s", seen.append) as t:
+        pass
+    assert len(seen) == 1 and seen[0].startswith("took ") and t.seconds >= 0.0
+    with pytest.raises(ValueError):            # nothing is logged when the block raises
+        with timed("never %.1f", seen.append):
+            raise ValueError("x")
+    assert len(seen) == 1
