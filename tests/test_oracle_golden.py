@@ -175,3 +175,19 @@ def test_restated_loops_edge_sizes(n, A):
     assert r.center_indices[0] == 0
     assert len(r.center_indices) == min(n, 4)
     assert np.all(r.assignments >= 0)
+
+
+def test_kmedoids_update_mpi_numpy_golden():
+    """test_cluster.py:422-463 seen from one rank: blobs (random_state=1, 20 samples), squared
+    euclid, k-centers k=3, proposals = the first point of every TRUE blob label -> medoids
+    [0, 3, 19]; the sweep's result equals a brute-force assignment."""
+    from sklearn.datasets import make_blobs
+    X, y = make_blobs(centers=[(0, 0), (0, 10), (10, 0)], random_state=1, n_samples=20)
+    r = oc.kcenters(X, od.sqeuclidean, n_clusters=3)
+    props = [int(np.where(y == cid)[0][0]) for cid in range(3)]
+    ind, d, a, _ = oc.pam_update(X, od.sqeuclidean, list(r.center_indices), r.assignments.copy(),
+                                 r.distances.copy(), proposals=props, random_state=0)
+    assert_array_equal(ind, [0, 3, 19])
+    ea, ed = oc.assign_to_nearest_center(X, X[[int(i) for i in ind]], od.sqeuclidean)
+    assert_array_equal(a, ea)
+    assert_allclose(d, ed, rtol=1e-6, atol=1e-3)
