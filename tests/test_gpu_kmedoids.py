@@ -251,3 +251,20 @@ def test_pam_pruned_full_pass_changes_nothing(cuda):
         assert_array_equal(out[0][1], out[1][1])
         assert_array_equal(out[0][2], out[1][2])
         assert out[0][3] == out[1][3]        # same proposals, same costs, same decisions
+
+
+def test_kmedoids_update_mpi_numpy_golden(cuda):
+    """enspara/test/test_cluster.py:422-463 on one rank: blobs (random_state=1, 20 samples),
+    squared euclid, proposals = the first point of every true label -> medoids [0, 3, 19]."""
+    from sklearn.datasets import make_blobs
+    from enspara_b200.cluster import kcenters, kmedoids, util
+    X, y = make_blobs(centers=[(0, 0), (0, 10), (10, 0)], random_state=1, n_samples=20)
+    r = kcenters.kcenters(X, "sqeuclidean", n_clusters=3)
+    props = [int(np.where(y == cid)[0][0]) for cid in range(3)]
+    ind, dists, assig, _ = kmedoids._kmedoids_pam_update(
+        X, "sqeuclidean", r.center_indices, r.assignments, r.distances, proposals=props,
+        random_state=0)
+    assert_array_equal(ind, [0, 3, 19])
+    ea, ed = util.assign_to_nearest_center(X, X[[int(i) for i in ind]], "sqeuclidean")
+    assert_array_equal(assig, ea)
+    assert_allclose(dists, ed, rtol=1e-06, atol=1e-03)
