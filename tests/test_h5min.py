@@ -74,7 +74,7 @@ def test_ra_load_rejects_mismatched_nodes(tmp_path):
         ra.load(p)
 
 
-def _chunked_file(path, arr, chunk_rows):
+def _chunked_file(path, arr, chunk_rows, leaf_size=0):
     """Hand-assemble a PyTables-style file: one chunked dataset with shuffle + deflate, to
     exercise the reader's B-tree / filter path without PyTables."""
     h5min.write(path, {"x": arr})          # start from a valid file, then graft a chunked one
@@ -99,16 +99,36 @@ def _chunked_file(path, arr, chunk_rows):
         base.extend(b"\0" * (-len(base) % 8))
         addrs.append(len(base))
         base.extend(comp)
-    base.extend(b"\0" * (-len(base) % 8))
-    btree = len(base)
-    node = bytearray(b"TREE" + struct.pack("<BBHQQ", 1, 0, len(chunks),
-                                           0xFFFFFFFFFFFFFFFF, 0xFFFFFFFFFFFFFFFF))
-    for (lo, comp), a in zip(chunks, addrs):
-        node += struct.pack("<II", len(comp), 0)
-        node += struct.pack("<%dQ" % (rank + 1), lo, *([0] * rank))
-        node += struct.pack("<Q", a)
-    node += struct.pack("<II", 0, 0) + struct.pack("<%dQ" % (rank + 1), n, *([0] * rank))
-    base.extend(node)
+    def leaf(entries):
+        base.extend(b"\0" * (-len(base) % 8))
+        at = len(base)
+        node = bytearray(b"TREE" + struct.pack("<BBHQQ", 1, 0, len(entries),
+                                               0xFFFFFFFFFFFFFFFF, 0xFFFFFFFFFFFFFFFF))
+        for (lo, comp), a in entries:
+            node += struct.pack("<II", len(comp), 0)
+            node += struct.pack("<%dQ" % (rank + 1), lo, *([0] * rank))
+            node += struct.pack("<Q", a)
+        node += struct.pack("<II", 0, 0) + struct.pack("<%dQ" % (rank + 1), n, *([0] * rank))
+        base.extend(node)
+        return at
+
+    entries = list(zip(chunks, addrs))
+    if leaf_size and len(entries) > leaf_size:
+        # two-level tree: leaves of `leaf_size` chunks under one internal node (level 1)
+        kids = [(entries[i][0][0], leaf(entries[i:i + leaf_size]))
+                for i in range(0, len(entries), leaf_size)]
+        base.extend(b"\0" * (-len(base) % 8))
+        btree = len(base)
+        node = bytearray(b"TREE" + struct.pack("<BBHQQ", 1, 1, len(kids),
+                                               0xFFFFFFFFFFFFFFFF, 0xFFFFFFFFFFFFFFFF))
+        for lo, at in kids:
+            node += struct.pack("<II", 0, 0)
+            node += struct.pack("<%dQ" % (rank + 1), lo, *([0] * rank))
+            node += struct.pack("<Q", at)
+        node += struct.pack("<II", 0, 0) + struct.pack("<%dQ" % (rank + 1), n, *([0] * rank))
+        base.extend(node)
+    else:
+        btree = leaf(entries)
     # new object header for the dataset: dataspace, datatype, filters, chunked layout
     space = struct.pack("<BBBBI", 1, rank, 0, 0, 0) + struct.pack("<%dQ" % rank, *arr.shape)
     filt = struct.pack("<BB6x", 1, 2)
@@ -140,6 +160,14 @@ def test_reads_chunked_shuffled_deflated_nodes(tmp_path, dtype, shape, chunk):
     got = h5min.read(p, "x")
     assert got.dtype == arr.dtype
     assert_array_equal(got, arr)
+
+
+def test_reads_two_level_chunk_btrees(tmp_path):
+    """Large PyTables arrays index their chunks with multi-level B-trees."""
+    arr = np.arange(97 * 5, dtype=np.float64).reshape(97, 5)
+    p = str(tmp_path / "deep.h5")
+    _chunked_file(p, arr, 4, leaf_size=3)       # 25 chunks, 9 leaves under one internal node
+    assert_array_equal(h5min.read(p, "x"), arr)
 
 
 @pytest.mark.reference
