@@ -8,8 +8,10 @@ heap), contiguous / compact / chunked (B-tree v1) layouts, deflate + shuffle (+ 
 skipped) filters, fixed-point and floating-point datatypes.  That is what PyTables / h5py write
 by default (``libver='earliest'``).  Anything else raises ``H5FormatError`` loudly.
 
-Writer: superblock v0, one root group, contiguous numeric datasets (no filters) -- enough for
-``ra.save`` style outputs that ``h5py`` / PyTables / this reader can load back.
+Writer: superblock v0, one root group, contiguous numeric datasets (no filters), laid out after
+the HDF5 file-format specification (version 0 structures) for ``ra.save`` style outputs.  Verified
+in this repository only by reading the files back with the reader above -- libhdf5 / h5py /
+PyTables are not available in the build image to cross-check.
 """
 import struct
 import zlib
@@ -428,8 +430,8 @@ def _msg(mtype, body, flags=0):
 
 
 def write(path, arrays):
-    """Write ``{name: ndarray}`` as contiguous datasets of the root group (HDF5 1.8-readable:
-    superblock v0, v1 object headers, one symbol-table node)."""
+    """Write ``{name: ndarray}`` as contiguous datasets of the root group (superblock v0, v1
+    object headers, one symbol-table node)."""
     names = sorted(arrays)
     if len(names) > 2 * 16:
         # one leaf node holds 2K entries; grow K instead of building a deeper tree
