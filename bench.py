@@ -52,6 +52,8 @@ def parse():
                    help="target CPU seconds for the bounded cpu_baseline sample")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-parity-check", action="store_true",
+                   help="skip the untimed N-rank == 1-rank check (N > 1)")
     p.add_argument("--fast", action="store_true", help="float32-block accumulation mode")
     return p.parse_args()
 
@@ -131,34 +133,21 @@ def measured_peaks():
 # CPU arm: the reference's path for this metric, restated (oracle/), bounded sample
 # ---------------------------------------------------------------------------------------------
 def _host_sample(n, n_atoms):
-    """The first n frames of the synthetic trajectory as a host array (generated on the GPU
-    when there is one -- the generators are bit-identical -- because the numpy generator takes
-    minutes at this size; generation is outside every timed region)."""
-    from enspara_b200 import synth
-    try:
-        import torch
-        if torch.cuda.is_available():
-            out = np.empty((n, n_atoms, 3), dtype=np.float32)
-            base = synth.base_conformers(n_atoms, 64, 0)
-            chunk = 125_000
-            for lo in range(0, n, chunk):
-                m = min(chunk, n - lo)
-                out[lo:lo + m] = synth.device_trajectory_aos(m, n_atoms, 0, lo,
-                                                             base=base).cpu().numpy()
-            torch.cuda.empty_cache()
-            return out
-    except Exception:
-        pass
-    return synth.trajectory(n, n_atoms, seed=0)
+    """The first n frames of the synthetic trajectory as a host array, made by the oracle's C
+    restatement of the generator (bit-identical to enspara_b200/synth.py and to the CUDA
+    generator; OpenMP, about a second).  The CPU arms therefore neither load the product's
+    CUDA library nor touch the GPU; generation is outside every timed region."""
+    from oracle import distances as od
+    return od.synth_trajectory(n, n_atoms, seed=0, first_frame=0)
 
 
 def cpu_kcenters_rate(n_atoms, steps, warmup, target_seconds, sample_frames=None):
     """Times the restated reference k-centers iteration (kcenters.py:282-309 around the
     restated md.rmsd with its per-call copy + centre) on all host threads.  Returns
     (evals_per_s, info dict)."""
-    from enspara_b200 import synth
     from oracle import distances as od
-    threads = od.num_threads()
+    # every core this process may use, whatever OMP_NUM_THREADS says (torchrun exports 1)
+    threads = od.use_all_cores()
     n = sample_frames or 250_000
     X = _host_sample(n, n_atoms)
     T = od.Trajectory(X)
@@ -168,7 +157,7 @@ def cpu_kcenters_rate(n_atoms, steps, warmup, target_seconds, sample_frames=None
 
     def iteration():
         new = int(np.argmax(distances))
-        d = od.rmsd_f32(T, T[new])
+        d = od.rmsd_f32_sse(T, T[new])
         upd = d < distances
         distances[upd] = d[upd]
         assignments[upd] = len(ctr)
@@ -189,9 +178,9 @@ def cpu_kcenters_rate(n_atoms, steps, warmup, target_seconds, sample_frames=None
     rate = n * steps / dt
     info = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": "%d k-centers iterations over %d frames x %d atoms (restated mdtraj "
-                      "float32 RMSD incl. per-call copy+centre, numpy bookkeeping as "
-                      "kcenters.py:282-309; mdtraj itself is not installable offline)"
-                      % (steps, n, n_atoms),
+                      "float32 RMSD: SSE 4-atom lanes + OpenMP over frames, incl. mdtraj's "
+                      "per-call copy+centre; numpy bookkeeping as kcenters.py:282-309; mdtraj "
+                      "itself is not installable offline)" % (steps, n, n_atoms),
             "seconds": dt}
     return rate, info, steps, dt
 
@@ -218,6 +207,59 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------
+# N ranks == 1 rank (the reference's own MPI bar: test_cluster.py:270-275, 309-314)
+# ---------------------------------------------------------------------------------------------
+def _checksum(center_list, assign, dist, first_index):
+    """Order-sensitive 63-bit checksum of (global centre list, assignments, float32 distance
+    bits) that is ADDITIVE over shards, so the sharded run's value is an all-reduce of the
+    ranks' values and must equal the single-GPU value of the same global data."""
+    g = np.arange(first_index, first_index + len(assign), dtype=np.int64)
+    bits = np.asarray(dist, dtype=np.float32).view(np.int32).astype(np.int64)
+    s = int(((np.asarray(assign, np.int64) + 2) * (g % 65521 + 1)).sum())
+    s += int(((bits % 65521) * (g % 65519 + 1)).sum())
+    c = int(sum((int(v) % 1000003) * (i + 1) for i, v in enumerate(center_list)))
+    return s, c
+
+
+def sharded_parity_check(world, rank, A, per_rank=40_000, n_centers=12):
+    """Untimed.  A down-scaled copy of the bench's global trajectory (per_rank frames per rank,
+    still large enough for the TMA step kernel + the exchange that the timed steps use) is
+    clustered twice through the public function: sharded over the N ranks, and in one piece on
+    every rank's own GPU (the generator is counter-based, so any rank can make all of it).
+    Centres, assignments and distances must be IDENTICAL."""
+    import torch
+    import torch.distributed as dist
+    from enspara_b200 import _lib, synth
+    from enspara_b200.cluster import kcenters as kc
+    full = synth.device_trajectory(per_rank * world, A, seed=0, first_frame=0)
+    mine = synth.device_trajectory(per_rank, A, seed=0, first_frame=rank * per_rank)
+    one = kc.kcenters(full, "rmsd", n_clusters=n_centers, mpi_mode=False)
+    shd, eng = kc.kcenters(mine, "rmsd", n_clusters=n_centers, mpi_mode=True,
+                           _return_engine=True)
+    lo, hi = rank * per_rank, (rank + 1) * per_rank
+    glob = [int(r * per_rank + l) for r, l in shd.center_indices]
+    ok_c = glob == [int(c) for c in one.center_indices]
+    ok_a = bool(np.array_equal(shd.assignments, one.assignments[lo:hi]))
+    ok_d = bool(np.array_equal(shd.distances, one.distances[lo:hi]))
+    s_sh, c_sh = _checksum(glob, shd.assignments, shd.distances, lo)
+    s_one, c_one = _checksum(one.center_indices, one.assignments, one.distances, 0)
+    t = torch.tensor([s_sh, int(ok_c), int(ok_a), int(ok_d)], dtype=torch.int64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    s_sh_all, n_c, n_a, n_d = (int(v) for v in t.cpu())
+    return {"what": "KCenters rmsd n_clusters=%d on a %d-frame x %d-atom down-scaled copy of "
+                    "the bench trajectory: %d-rank sharded run vs single-GPU run"
+                    % (n_centers, per_rank * world, A, world),
+            "frames_total": per_rank * world, "frames_per_rank": per_rank,
+            "step_kernel_is_tma": bool(_lib.load().eb_kcenters_step_rmsd_uses_tma(per_rank, A)),
+            "exchange_is_fused_p2p": bool(eng.p2p),
+            "centers_equal": n_c == world, "assignments_equal": n_a == world,
+            "distances_equal": n_d == world,
+            "checksum_sharded": [s_sh_all, c_sh], "checksum_single_gpu": [s_one, c_one],
+            "equal": bool(n_c == world and n_a == world and n_d == world
+                          and s_sh_all == s_one and c_sh == c_one)}
+
+
+# ---------------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------------
 def run_b200(args):
@@ -240,7 +282,11 @@ def run_b200(args):
     sys.stdout.flush()
     saved_stdout = os.dup(1)
     os.dup2(2, 1)
+    numa_cpus = 0
     if world > 1:
+        # one process per GPU, all uploading at once in the e2e leg: keep each process (and
+        # the pinned buffers it first-touches) on its GPU's NUMA node
+        numa_cpus = mpi.bind_to_gpu_numa_node(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     comm = mpi.comm if world > 1 else kc_mod._SingleComm()
 
@@ -292,6 +338,16 @@ def run_b200(args):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     total_ms = float(tmax.cpu()[0])
     value = n_total * K / (total_ms * 1e-3)
+
+    exch_wait_us = None
+    if world > 1 and eng.p2p:
+        # time block 0 spent in the prologue waiting for the peers' records, per step since
+        # the seed (the spread between the GPUs: every iteration waits for the slowest shard)
+        exch_wait_us = 1e-3 * float(st.wait_ns) / max(1, K + W)
+
+    parity = None
+    if world > 1 and not args.no_parity_check:
+        parity = sharded_parity_check(world, rank, A)
 
     # roofline of the dominant kernel (the fused step): algorithmic bytes per launch
     # = (12*A + 8) bytes per frame x frames per launch, over the mean per-launch
@@ -350,10 +406,16 @@ def run_b200(args):
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         dt = float(tm.cpu()[0])
         assert len(est.result_.center_indices) == K2
+        # where the time goes (second, UNTIMED fit with a device sync after every phase)
+        os.environ["ENSPARA_B200_PHASE_TIMES"] = "1"
+        KCenters("rmsd", n_clusters=K2, mpi_mode=(world > 1)).fit(host_np)
+        os.environ["ENSPARA_B200_PHASE_TIMES"] = "0"
+        phases = {k: round(v, 4) for k, v in kc_mod.last_phase_times.items()}
         e2e = {"value": n_total * K2 / dt, "unit": UNIT,
                "h2d_bytes_per_step": int(n_local * A * 12 / K2),
                "d2h_bytes_per_step": int(n_local * (4 + 4) / K2),
-               "seconds": dt, "steps": K2,
+               "seconds": dt, "steps": K2, "phases_s_rank0_untimed_rerun": phases,
+               "numa_bound_cpus": numa_cpus,
                "what": "KCenters('rmsd', n_clusters=%d).fit(pinned host (n,%d,3) float32): "
                        "H2D + centring + %d iterations + D2H of assignments/distances, per "
                        "rank on its shard" % (K2, A, K2)}
@@ -384,10 +446,16 @@ def run_b200(args):
             "roofline": roofline, "clocks": clk, "gpu_launches": K,
             "e2e": e2e, "cpu_baseline": cpu,
         }
+        if parity is not None:
+            line["parity_check"] = parity
+        if exch_wait_us is not None:
+            line["exchange_wait_us_per_step"] = exch_wait_us
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if parity is not None and not parity["equal"]:
+        sys.exit("bench.py: the %d-rank run differs from the single-GPU run" % world)
 
 
 def main():

@@ -20,7 +20,8 @@ class KcState(ctypes.Structure):
     _fields_ = [("n_centers", ctypes.c_int32), ("done", ctypes.c_int32),
                 ("blocks_done", ctypes.c_uint32), ("n_noop", ctypes.c_int32),
                 ("maxdist", ctypes.c_double), ("local_maxdist", ctypes.c_double),
-                ("last_center", ctypes.c_int64), ("reserved", ctypes.c_int64 * 3)]
+                ("last_center", ctypes.c_int64), ("error", ctypes.c_int64),
+                ("wait_ns", ctypes.c_int64), ("reserved", ctypes.c_int64)]
 
 
 assert ctypes.sizeof(KcState) == 64

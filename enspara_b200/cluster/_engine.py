@@ -18,13 +18,22 @@ _INT32_MAX = 2 ** 31 - 1
 
 class ShardInfo:
     """Where this rank's frames sit in the global order: contiguous blocks by rank, so that
-    'lowest rank, then lowest local index' (kcenters.py:337-338) == lowest global index."""
+    'lowest rank, then lowest local index' (kcenters.py:337-338) == lowest global index.
 
-    def __init__(self, n_local, comm):
+    ``extra`` is an int this rank contributes alongside its length (the engine's "peer-memory
+    exchange is set up" bit), so ONE small tensor all-gather carries everything the ranks have
+    to agree on -- no pickled host collectives."""
+
+    def __init__(self, n_local, comm, extra=0, device=None):
         self.comm = comm
         self.size = comm.size
         self.rank = comm.rank
-        lens = comm.all_gather_object(int(n_local))
+        if self.size == 1:
+            lens, extras = [int(n_local)], [int(extra)]
+        else:
+            both = gather_int_pairs(comm, int(n_local), int(extra), device)
+            lens, extras = both[:, 0].tolist(), both[:, 1].tolist()
+        self.extras = [int(e) for e in extras]
         self.lengths = np.asarray(lens, dtype=np.int64)
         self.offsets = np.concatenate([[0], np.cumsum(self.lengths)]).astype(np.int64)
         self.offset = int(self.offsets[self.rank])
@@ -33,6 +42,44 @@ class ShardInfo:
     def to_rank_local(self, global_idx):
         r = int(np.searchsorted(self.offsets, global_idx, side="right") - 1)
         return r, int(global_idx - self.offsets[r])
+
+
+def gather_int_pairs(comm, a, b, device=None):
+    """(size, 2) int64 numpy array of every rank's (a, b): one tensor all-gather (NCCL on the
+    device, gloo on the host) instead of ``all_gather_object``'s pickle + two collectives."""
+    import torch.distributed as dist
+    on_gpu = dist.get_backend(getattr(comm, "group", None)) == "nccl"
+    if on_gpu:
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    else:
+        dev = torch.device("cpu")
+    mine = torch.tensor([int(a), int(b)], dtype=torch.int64, device=dev)
+    out = torch.empty(2 * comm.size, dtype=torch.int64, device=dev)
+    comm.all_gather_into(out, mine)
+    return out.cpu().numpy().reshape(comm.size, 2)
+
+
+class _ExchangePool:
+    """Symmetric exchange buffers of the fused peer-memory candidate exchange, kept per
+    (process group, buffer size).  Allocation + rendezvous of torch symmetric memory costs
+    0.1-0.3 s (CUDA VMM mapping into every peer), so an engine borrows a buffer for a run and
+    hands it back when the run ended cleanly; the sequence numbers inside simply continue
+    (a flag is compared for equality with the consumer's own publish counter, and every rank
+    makes the same sequence of publishes).  A run that raised keeps its buffer, which is then
+    never reused."""
+
+    def __init__(self):
+        self.free = {}
+
+    def take(self, key):
+        lst = self.free.get(key)
+        return lst.pop() if lst else None
+
+    def give(self, key, item):
+        self.free.setdefault(key, []).append(item)
+
+
+_exchange_pool = _ExchangePool()
 
 
 class KCentersEngine:
@@ -48,10 +95,20 @@ class KCentersEngine:
         self.exact = bool(exact)
         self.lib = _lib.load()
         self.n = len(data)
-        self.shard = ShardInfo(self.n, comm)
         self.is_rmsd = isinstance(data, DeviceTrajectory)
         dev = data.xyz.device if self.is_rmsd else data.X.device
         self.dev = dev
+        # use_triangle_inequality (kcenters.py:287-296): RMSD only; needs the coordinates of the
+        # centres chosen so far (center_store) and the new centre's distance to each (cc)
+        self.triangle = bool(triangle) and self.is_rmsd and self.exact
+        # sharded RMSD runs exchange the candidate records through peer memory inside the step
+        # kernel (no collective launch); anything else uses one NCCL all-gather per step.
+        # Every rank must take the same path: the "set up" bit travels with the shard lengths.
+        p2p_ready = self._setup_p2p()
+        self.shard = ShardInfo(self.n, comm, extra=int(p2p_ready), device=dev)
+        self.p2p = bool(p2p_ready) and all(self.shard.extras)
+        if p2p_ready and not self.p2p:
+            self._release_p2p(reusable=True)
         if self.is_rmsd:
             self.rec_bytes = int(self.lib.eb_rmsd_record_bytes(data.n_atoms))
             self.dist = torch.full((self.n,), float("inf"), dtype=torch.float32, device=dev)
@@ -71,50 +128,56 @@ class KCentersEngine:
         self.center_list = None
         self._state_host = torch.empty(64, dtype=torch.uint8).pin_memory()
         self.launches = 0
-        # use_triangle_inequality (kcenters.py:287-296): RMSD only; needs the coordinates of the
-        # centres chosen so far (center_store) and the new centre's distance to each (cc)
-        self.triangle = bool(triangle) and self.is_rmsd and self.exact
         self.center_store = self.center_store_traces = self.cc = None
         self._queued = 0            # host upper bound of the number of centres
-        # sharded RMSD runs exchange the candidate records through peer memory inside the step
-        # kernel (no collective launch); anything else uses one NCCL all-gather per step
-        self.p2p = self._setup_p2p()
 
     # -- fused peer-memory exchange --------------------------------------------------------
     def _setup_p2p(self):
-        """Symmetric exchange buffers (torch symmetric memory: CUDA VMM + peer mapping) for the
-        fused step + exchange kernels.  Every rank must take the same path, so the decision is
-        agreed on with one collective; any failure falls back to the NCCL all-gather."""
+        """Borrow (or create) the symmetric exchange buffer (torch symmetric memory: CUDA VMM +
+        peer mapping) for the fused step + exchange kernels.  True when this rank is ready; the
+        engine then agrees with its peers (ShardInfo.extras) and falls back to the NCCL
+        all-gather unless every rank is."""
         import logging
         import os
-        sh = self.shard
-        if sh.size <= 1:
+        size = self.comm.size
+        self._exch = None
+        if size <= 1:
             return False
-        want = (self.is_rmsd and not self.triangle and sh.size <= 8
+        want = (self.is_rmsd and not self.triangle and size <= 8
                 and os.environ.get("ENSPARA_B200_P2P", "1") != "0")
-        ok, err = False, None
-        if want:
+        if not want:
+            return False
+        nbytes = int(self.lib.eb_exch_bytes(self.data.n_atoms, size))
+        self._exch_key = (id(getattr(self.comm, "group", None)), size, nbytes, str(self.dev))
+        item = _exchange_pool.take(self._exch_key)
+        if item is None:
             try:
                 import torch.distributed as dist
                 import torch.distributed._symmetric_memory as symm
-                nbytes = int(self.lib.eb_exch_bytes(self.data.n_atoms, sh.size))
+                group = getattr(self.comm, "group", None) or dist.group.WORLD
                 buf = symm.empty(nbytes, dtype=torch.uint8, device=self.dev)
-                hdl = symm.rendezvous(buf, dist.group.WORLD)
+                hdl = symm.rendezvous(buf, group)
                 buf.zero_()
-                self._exch_buf, self._exch_hdl = buf, hdl
-                self._exch_peers = torch.tensor([int(p) for p in hdl.buffer_ptrs],
-                                                dtype=torch.int64, device=self.dev)
-                ok = True
+                peers = torch.tensor([int(p) for p in hdl.buffer_ptrs], dtype=torch.int64,
+                                     device=self.dev)
+                torch.cuda.synchronize()
+                dist.barrier(group)   # every buffer is zeroed before anyone publishes into it
+                item = (buf, hdl, peers)
             except Exception as exc:  # no peer access, old torch, ...
-                err = exc
-        all_ok = all(self.comm.all_gather_object(bool(ok)))
-        if want and not all_ok and sh.rank == 0:
-            logging.getLogger(__name__).warning(
-                "peer-memory candidate exchange unavailable (%r); using the NCCL all-gather", err)
-        if all_ok:
-            torch.cuda.synchronize()
-            self.comm.barrier()      # every buffer is zeroed before anyone publishes into it
-        return bool(all_ok)
+                logging.getLogger(__name__).warning(
+                    "peer-memory candidate exchange unavailable (%r); using the NCCL "
+                    "all-gather", exc)
+                return False
+        self._exch = item
+        self._exch_buf, self._exch_hdl, self._exch_peers = item
+        return True
+
+    def _release_p2p(self, reusable):
+        """Hand the exchange buffer back.  ``reusable`` only after a cleanly finished run: all
+        ranks have passed the final collective, so nobody still reads or writes the buffer."""
+        item, self._exch = self._exch, None
+        if item is not None and reusable:
+            _exchange_pool.give(self._exch_key, item)
 
     # -- state ---------------------------------------------------------------------------
     def set_state(self, distances, assignments):
@@ -127,7 +190,14 @@ class KCentersEngine:
     def read_state(self):
         self._state_host.copy_(self.state, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return _lib.KcState.from_buffer_copy(self._state_host.numpy().tobytes())
+        st = _lib.KcState.from_buffer_copy(self._state_host.numpy().tobytes())
+        if st.error:
+            self._release_p2p(reusable=False)
+            raise RuntimeError(
+                "enspara_b200: the peer-memory candidate exchange timed out on rank %d (a peer "
+                "rank died or queued a different launch sequence); the run is void. "
+                "ENSPARA_B200_P2P=0 selects the NCCL all-gather exchange." % self.shard.rank)
+        return st
 
     # -- launches ------------------------------------------------------------------------
     def _exchange(self):
@@ -136,6 +206,9 @@ class KCentersEngine:
 
     def seed(self, first_center_id=0):
         s = stream_ptr()
+        if self.p2p and self._exch is None:      # a second run of the same engine
+            self.p2p = self._setup_p2p()
+            assert self.p2p, "peer-memory exchange could not be re-acquired"
         if self.p2p:
             d = self.data
             _lib.call("eb_kcenters_seed_rmsd_p2p", ptr(d.xyz), ptr(d.traces), self.n, d.n_atoms,
@@ -243,7 +316,7 @@ class KCentersEngine:
         cutoff = 0.0 if dist_cutoff is None else float(dist_cutoff)
         self.seed(n_existing)
         if limit <= n_existing or n_global == 0:
-            return [], self._global_maxdist()
+            return [], self._finish()
         bounded = limit < _INT32_MAX
         # the centre list grows geometrically when only a cutoff bounds the run; a run can
         # never choose more new centres than there are frames
@@ -271,7 +344,16 @@ class KCentersEngine:
                 break
         k = int(st.n_centers)
         centers = self.center_list[n_existing:k].cpu().numpy().astype(np.int64)
-        return [int(c) for c in centers], self._global_maxdist()
+        self.wait_ns = int(st.wait_ns)
+        return [int(c) for c in centers], self._finish()
+
+    def _finish(self):
+        """End of a run: the global max-min-distance (a collective every rank passes only after
+        every rank's last step has completed), after which the exchange buffer is idle on all
+        ranks and can go back to the pool."""
+        m = self._global_maxdist()
+        self._release_p2p(reusable=True)
+        return m
 
     def _global_maxdist(self):
         st = self.read_state()

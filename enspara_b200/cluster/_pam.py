@@ -195,6 +195,17 @@ class PamEngine:
         ``max_proposals`` stops after that many clusters (benchmarks only)."""
         rs = check_random_state(random_state)
         sh = self.shard
+        if sh.size > 1 and proposals is None:
+            # Every rank derives owner / k-th member / broadcast root from its own draw, so all
+            # ranks must consume ONE random stream: rank 0's (the reference: rank 0 draws and
+            # broadcasts the index, mpi/ops.py:247-253).  With random_state=None the ranks'
+            # global RandomStates are seeded differently; one broadcast of rank 0's generator
+            # state per sweep aligns them, and a seeded run still equals the serial run.
+            state = self.comm.broadcast_object(rs.get_state() if sh.rank == 0 else None, 0)
+            if sh.rank != 0:
+                if rs is np.random.mtrand._rand:     # do not clobber the process-global state
+                    rs = np.random.RandomState()
+                rs.set_state(state)
         acceptances = 0
         prof = self.profile          # None, or dict phase -> seconds (developer timing)
 

@@ -16,6 +16,29 @@ from ._engine import KCentersEngine
 
 logger = logging.getLogger(__name__)
 
+#: phase -> seconds of the last kcenters() call when ENSPARA_B200_PHASE_TIMES=1 (developer
+#: timing: each mark synchronises the device, so it is off by default)
+last_phase_times = {}
+
+
+class _Phases:
+    def __init__(self):
+        import os
+        self.on = os.environ.get("ENSPARA_B200_PHASE_TIMES", "0") == "1"
+        self.t = time.perf_counter()
+        self.d = {}
+
+    def mark(self, name):
+        if not self.on:
+            return
+        import torch
+        torch.cuda.synchronize()
+        now = time.perf_counter()
+        self.d[name] = self.d.get(name, 0.0) + now - self.t
+        self.t = now
+        last_phase_times.clear()
+        last_phase_times.update(self.d)
+
 
 class KCenters(BaseEstimator, ClusterMixin, util.MolecularClusterMixin):
     """Sklearn-style k-centers (Gonzalez 1985) -- reference: kcenters.py:18-100.
@@ -113,10 +136,13 @@ def kcenters(traj, distance_method, n_clusters=np.inf, dist_cutoff=0, init_cente
         raise NotImplementedError(
             "We haven't implemented kcenters 'random_first_center' yet.")
 
+    ph = _Phases()
     data = metric.to_device(traj)
+    ph.mark("upload+centre")
     comm = mpi.comm if mpi_mode else _SingleComm()
     engine = KCentersEngine(data, metric.kind, comm, exact=exact,
                             triangle=use_triangle_inequality)
+    ph.mark("engine_setup")
 
     centers = []
     ctr_inds = []
@@ -131,6 +157,16 @@ def kcenters(traj, distance_method, n_clusters=np.inf, dist_cutoff=0, init_cente
         a_host, d_host = engine.results_host()
         ctr_inds = list(util.find_cluster_centers(a_host, d_host))
         n_existing = len(ctr_inds)
+        if mpi_mode and comm.size > 1:
+            # a shard without members of some initial centre would count fewer existing
+            # centres than its peers and then use other centre ids, launch counts and
+            # collectives: agree on the labels present on ANY rank (one small all-reduce)
+            import torch
+            present = torch.zeros(max(len(centers), 1), dtype=torch.int32, device=engine.dev)
+            if len(a_host):
+                present[torch.as_tensor(np.unique(a_host), device=engine.dev)] = 1
+            comm.all_reduce_max(present)
+            n_existing = int(present.sum().item())
         if n_existing == len(centers):
             engine.preload_centers(cdev)
         else:
@@ -139,6 +175,7 @@ def kcenters(traj, distance_method, n_clusters=np.inf, dist_cutoff=0, init_cente
             engine.triangle = False
 
     new_global, maxdist = engine.run(n_clusters, dist_cutoff, n_existing=n_existing)
+    ph.mark("iterations")
 
     if mpi_mode:
         new_inds = [engine.shard.to_rank_local(g) for g in new_global]
@@ -151,7 +188,9 @@ def kcenters(traj, distance_method, n_clusters=np.inf, dist_cutoff=0, init_cente
 
     logger.info("Terminated k-centers with n=%s and d=%0.6f.", len(ctr_inds), maxdist)
 
+    ph.mark("centres")
     assignments, distances = engine.results_host()
+    ph.mark("results_d2h")
     result = util.ClusterResult(center_indices=ctr_inds, assignments=assignments,
                                 distances=distances, centers=centers)
     if _return_engine:
@@ -166,6 +205,9 @@ class _SingleComm:
 
     def all_gather_object(self, obj):
         return [obj]
+
+    def broadcast_object(self, obj, root=0):
+        return obj
 
     def all_gather_into(self, out, inp):
         if out.data_ptr() != inp.data_ptr():

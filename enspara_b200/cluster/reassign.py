@@ -47,6 +47,13 @@ def compute_batches(lengths, batch_size):
     return batch_indices
 
 
+def nonempty_batches(lengths, batch_size):
+    """``compute_batches`` without the empty batch it opens with when the first file alone
+    fills one (``lengths[0] >= batch_size``, e.g. ``[100, 10, 20]`` at 100 -> ``[[], [0],
+    [1, 2]]``): the streaming pass chains a prefetch from every batch to the next."""
+    return [b for b in compute_batches(lengths, batch_size) if b]
+
+
 #: beyond this many bytes per batch streaming gains nothing (the loader, the H2D copy and the
 #: kernels already overlap); smaller batches keep the two pinned staging buffers modest
 BATCH_BYTES_CAP = 8 << 30
@@ -191,7 +198,7 @@ def batch_reassign(targets, centers, lengths, frac_mem, n_procs=None, stats=None
         raise ImproperlyConfigured(
             "Batch size of %s was smaller than largest file (size %s)."
             % (batch_size, max(lengths)))
-    batches = compute_batches(lengths, batch_size)
+    batches = nonempty_batches(lengths, batch_size)
     metric = util.RMSD
     cdev = DeviceTrajectory.from_host(cxyz)          # centred once, resident for all batches
 
@@ -221,10 +228,8 @@ def batch_reassign(targets, centers, lengths, frac_mem, n_procs=None, stats=None
     t_load = t_gpu = 0.0
     pool = ThreadPoolExecutor(max_workers=1)
     try:
-        pending = pool.submit(load_batch, 0) if batches and batches[0] else None
+        pending = pool.submit(load_batch, 0) if batches else None
         for bi, batch in enumerate(batches):
-            if not batch:
-                continue
             tick = time.perf_counter()
             n_b = pending.result()
             t_load += time.perf_counter() - tick

@@ -161,6 +161,7 @@ struct Exch {
     int size;
     int rank;
     unsigned rec_stride;      // bytes between records (>= record bytes, multiple of 16)
+    unsigned long long timeout_ns;  // bounded spin: give up (state->error = 1) after this long
 };
 constexpr int kExchMaxRanks = 8;
 constexpr int kExchFlagsOff = 128;
@@ -179,19 +180,45 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
 
 // Consumer side (all threads of the block): wait until every rank's record of the current
 // sequence number has arrived in THIS rank's buffer; returns the local record array.
-__device__ __forceinline__ const unsigned char *exch_wait(const Exch &e)
+// The spin is bounded: if a peer's flag does not arrive within e.timeout_ns (a rank died or
+// queued a different launch sequence) every thread of the block gets nullptr, and the caller
+// marks the run failed instead of hanging the GPU.  `wait_ns` (thread 0) receives the time
+// spent waiting, for the per-step breakdown in eb_kc_state.
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ const unsigned char *exch_wait(const Exch &e,
+                                                          unsigned long long *wait_ns = nullptr)
 {
     unsigned char *me = reinterpret_cast<unsigned char *>(e.peers[e.rank]);
     const unsigned long long q = *reinterpret_cast<volatile unsigned long long *>(me);
     const int p = (int)(q & 1ull);
+    int bad = 0;
+    unsigned long long t_in = 0;
+    if (wait_ns && threadIdx.x == 0) t_in = globaltimer_ns();
     if ((int)threadIdx.x < e.size) {
         const unsigned long long *flag =
             reinterpret_cast<const unsigned long long *>(me + kExchFlagsOff) +
             p * kExchMaxRanks + threadIdx.x;
+        unsigned spins = 0;
+        unsigned long long t0 = 0;
         while (ld_acquire_sys(flag) != q) {
+            if ((++spins & 0x3ffu) == 0u) {
+                const unsigned long long t = globaltimer_ns();
+                if (t0 == 0) {
+                    t0 = t;
+                } else if (t - t0 > e.timeout_ns) {
+                    bad = 1;
+                    break;
+                }
+            }
         }
     }
-    __syncthreads();
+    if (__syncthreads_or(bad)) return nullptr;
+    if (wait_ns && threadIdx.x == 0) *wait_ns = globaltimer_ns() - t_in;
     return me + kExchRecordsOff + (size_t)p * e.size * e.rec_stride;
 }
 

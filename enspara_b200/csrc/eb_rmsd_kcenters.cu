@@ -179,7 +179,16 @@ k_kcenters_step_rmsd(const float *__restrict__ xyz, const double *__restrict__ t
                 if (MODE == kModeStep && blockIdx.x == 0 && threadIdx.x == 0) state->n_noop += 1;
                 return;
             }
-            cand_in = exch_wait(exch);
+            unsigned long long waited = 0;
+            cand_in = exch_wait(exch, &waited);
+            if (!cand_in) {   // a peer never published: fail the run instead of hanging
+                if (threadIdx.x == 0) {
+                    state->error = 1;
+                    state->done = 1;
+                }
+                return;
+            }
+            if (blockIdx.x == 0 && threadIdx.x == 0) state->wait_ns += (long long)waited;
             n_cand = exch.size;
             rec_bytes = exch.rec_stride;
         }
@@ -425,7 +434,16 @@ k_kcenters_step_rmsd_tma(const float *__restrict__ xyz, const double *__restrict
                 if (blockIdx.x == 0 && threadIdx.x == 0) state->n_noop += 1;
                 return;
             }
-            cand_in = exch_wait(exch);
+            unsigned long long waited = 0;
+            cand_in = exch_wait(exch, &waited);
+            if (!cand_in) {   // a peer never published: fail the run instead of hanging
+                if (threadIdx.x == 0) {
+                    state->error = 1;
+                    state->done = 1;
+                }
+                return;
+            }
+            if (blockIdx.x == 0 && threadIdx.x == 0) state->wait_ns += (long long)waited;
             n_cand = exch.size;
             rec_bytes = exch.rec_stride;
         }
@@ -917,6 +935,13 @@ static int make_exch(Exch *e, const void *peers_dev, int n_ranks, int rank, int 
     e->size = n_ranks;
     e->rank = rank;
     e->rec_stride = (unsigned)((rec + 127) & ~size_t(127));
+    // bounded spin (seconds, EB_EXCH_TIMEOUT_S; default 60): a step normally waits microseconds
+    static const double timeout_s = [] {
+        const char *v = getenv("EB_EXCH_TIMEOUT_S");
+        const double t = v ? atof(v) : 60.0;
+        return t > 0.0 ? t : 60.0;
+    }();
+    e->timeout_ns = (unsigned long long)(timeout_s * 1e9);
     return EB_OK;
 }
 

@@ -26,6 +26,37 @@ def size():
     return dist.get_world_size() if is_distributed() else 1
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process to the CPUs nearest to its GPU (NVML's ideal affinity), so that pinned
+    staging buffers are first-touched on the GPU's NUMA node: with one process per GPU all
+    uploading at once, remote-socket host memory is what limits host -> HBM throughput.
+    Best effort: returns the number of CPUs bound to, or 0 when NVML is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                phys = ids[device_index]
+                h = (pynvml.nvmlDeviceGetHandleByIndex(int(phys)) if phys.isdigit()
+                     else pynvml.nvmlDeviceGetHandleByUUID(phys))
+            else:
+                h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+            n_cpu = os.cpu_count() or 1
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+            cpus = {64 * w + b for w, mask in enumerate(words) for b in range(64)
+                    if (int(mask) >> b) & 1}
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+            return len(cpus)
+        finally:
+            pynvml.nvmlShutdown()
+    except Exception:
+        return 0
+
+
 def init_from_env(backend=None):
     """Initialise the default process group from torchrun's environment (idempotent)."""
     if is_distributed() or "RANK" not in os.environ:
@@ -33,7 +64,12 @@ def init_from_env(backend=None):
     if backend is None:
         backend = "nccl" if torch.cuda.is_available() else "gloo"
     if backend == "nccl":
-        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        if os.environ.get("ENSPARA_B200_NUMA_BIND", "1") != "0":
+            bind_to_gpu_numa_node(local)
+        dist.init_process_group(backend=backend, device_id=torch.device("cuda", local))
+        return
     dist.init_process_group(backend=backend)
 
 
@@ -77,6 +113,15 @@ class Comm:
         if self.size > 1:
             dist.broadcast(t, src=root, group=self.group)
         return t
+
+    def broadcast_object(self, obj, root=0):
+        """Pickled broadcast of a small host object (used once per PAM sweep for the
+        RandomState, never per proposal)."""
+        if self.size == 1:
+            return obj
+        box = [obj]
+        dist.broadcast_object_list(box, src=root, group=self.group)
+        return box[0]
 
     def all_gather_object(self, obj):
         if self.size == 1:

@@ -68,7 +68,11 @@ typedef struct eb_kc_state {
     double maxdist;       /* GLOBAL max of min-distances seen by the last step's prologue */
     double local_maxdist; /* max of min-distances on this shard after the last step       */
     int64_t last_center;  /* global index of the last centre chosen                       */
-    int64_t reserved[3];
+    int64_t error;        /* != 0: the peer-memory exchange timed out (a rank died or queued a
+                             different launch sequence); the run is void, later steps no-ops */
+    int64_t wait_ns;      /* fused exchange: ns block 0 spent waiting for the peers' records,
+                             summed over the steps since the seed (diagnostic)               */
+    int64_t reserved;
 } eb_kc_state; /* 64 bytes */
 
 int eb_version(void);

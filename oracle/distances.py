@@ -52,6 +52,12 @@ def lib():
         L.orc_kcenters_update_f32.restype = cl
         L.orc_kcenters_update_f32.argtypes = [vp, cl, cl, vp, vp]
         L.orc_num_threads.restype = ci
+        L.orc_synth_trajectory.restype = None
+        L.orc_synth_trajectory.argtypes = [vp, cl, ci, cl, ctypes.c_uint64, vp, ci]
+        L.orc_synth_features.restype = None
+        L.orc_synth_features.argtypes = [vp, cl, cl, cl, ctypes.c_uint64]
+        L.orc_set_num_threads.restype = None
+        L.orc_set_num_threads.argtypes = [ci]
         _lib = L
     return _lib
 
@@ -62,6 +68,18 @@ def _p(a):
 
 def num_threads():
     return int(lib().orc_num_threads())
+
+
+def use_all_cores():
+    """Set the OpenMP team to every core this process may run on, whatever OMP_NUM_THREADS
+    says (torchrun exports OMP_NUM_THREADS=1, which silently made the CPU arm single-threaded
+    at N > 1).  Returns the thread count now in use."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        n = os.cpu_count() or 1
+    lib().orc_set_num_threads(int(n))
+    return num_threads()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -138,8 +156,10 @@ def _make_rmsd(mode):
 
 #: float64-accumulation "truth" -- what the CUDA path is compared with
 rmsd = _make_rmsd(0)
-#: mdtraj-like float32 SSE-lane arithmetic -- timed CPU baseline, noise quantification
+#: mdtraj-like float32 4-atom-lane arithmetic, scalar emulation -- noise quantification
 rmsd_f32 = _make_rmsd(1)
+#: the same arithmetic with SSE intrinsics (bit-identical to rmsd_f32) -- timed CPU baseline
+rmsd_f32_sse = _make_rmsd(2)
 
 
 def rmsd_precentered(xyz, traces64, ref, ref_trace):
@@ -183,3 +203,20 @@ manhattan = _libdist("manhattan")
 def sqeuclidean(X, x):
     """The squared-euclid callable of the reference's own test (test_cluster.py:509-510)."""
     return np.square(X - x).sum(axis=1)
+
+
+def synth_trajectory(n, n_atoms, seed=0, first_frame=0, n_base=64):
+    """enspara_b200.synth.trajectory restated in C + OpenMP (bit-identical, seconds instead of
+    minutes): lets the CPU arms make their host sample without the product's CUDA library."""
+    from enspara_b200 import synth          # numpy only: the 64 base conformers are tiny
+    base = np.ascontiguousarray(synth.base_conformers(n_atoms, n_base, seed))
+    out = np.empty((n, n_atoms, 3), np.float32)
+    lib().orc_synth_trajectory(_p(out), n, n_atoms, first_frame, ctypes.c_uint64(seed), _p(base),
+                               n_base)
+    return out
+
+
+def synth_features(n, n_features, seed=0, first_row=0):
+    out = np.empty((n, n_features), np.float32)
+    lib().orc_synth_features(_p(out), n, n_features, first_row, ctypes.c_uint64(seed))
+    return out

@@ -199,9 +199,94 @@ void orc_rmsd_f32(const float *xyz, const float *traces32, long n, int A, const 
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* The same arithmetic with SSE intrinsics, the way mdtraj's msd_atom_major runs it (SURVEY.md */
+/* App. B step 3): 12 floats = 4 atoms are loaded as three vectors, shuffled AoS -> SoA, nine  */
+/* mulps + nine addps per step, one vector accumulator per matrix entry, horizontal add at the */
+/* end.  Lane l of accumulator e is exactly acc[e][l] of orc_rmsd_f32 above (mul and add round */
+/* separately, -ffp-contract=off), so the two are BIT-IDENTICAL (tests/test_oracle_golden.py); */
+/* this one is what the CPU baselines time.                                                   */
+/* ------------------------------------------------------------------------------------------ */
+#include <immintrin.h>
+static inline void aos4_to_soa(const float *p, __m128 *x, __m128 *y, __m128 *z)
+{
+    const __m128 a = _mm_loadu_ps(p);      /* x0 y0 z0 x1 */
+    const __m128 b = _mm_loadu_ps(p + 4);  /* y1 z1 x2 y2 */
+    const __m128 c = _mm_loadu_ps(p + 8);  /* z2 x3 y3 z3 */
+    const __m128 t0 = _mm_shuffle_ps(b, c, _MM_SHUFFLE(1, 0, 3, 2)); /* x2 y2 z2 x3 */
+    const __m128 t1 = _mm_shuffle_ps(a, b, _MM_SHUFFLE(1, 0, 3, 2)); /* z0 x1 y1 z1 */
+    *x = _mm_shuffle_ps(a, t0, _MM_SHUFFLE(3, 0, 3, 0));             /* x0 x1 x2 x3 */
+    *y = _mm_shuffle_ps(t1, c, _MM_SHUFFLE(2, 1, 2, 1));             /* y1.. fixed below */
+    /* y: y0 = a[1], y1 = b[0], y2 = b[3], y3 = c[2] */
+    {
+        const __m128 ay = _mm_shuffle_ps(a, b, _MM_SHUFFLE(0, 0, 1, 1));   /* y0 y0 y1 y1 */
+        const __m128 cy = _mm_shuffle_ps(b, c, _MM_SHUFFLE(2, 2, 3, 3));   /* y2 y2 y3 y3 */
+        *y = _mm_shuffle_ps(ay, cy, _MM_SHUFFLE(2, 0, 2, 0));              /* y0 y1 y2 y3 */
+    }
+    /* z: z0 = a[2], z1 = b[1], z2 = c[0], z3 = c[3] */
+    {
+        const __m128 az = _mm_shuffle_ps(a, b, _MM_SHUFFLE(1, 1, 2, 2));   /* z0 z0 z1 z1 */
+        const __m128 cz = _mm_shuffle_ps(c, c, _MM_SHUFFLE(3, 3, 0, 0));   /* z2 z2 z3 z3 */
+        *z = _mm_shuffle_ps(az, cz, _MM_SHUFFLE(2, 0, 2, 0));              /* z0 z1 z2 z3 */
+    }
+}
+
+static inline float hsum4(__m128 v)
+{
+    float l[4];
+    _mm_storeu_ps(l, v);
+    return (l[0] + l[1]) + (l[2] + l[3]);
+}
+
+void orc_rmsd_f32_sse(const float *xyz, const float *traces32, long n, int A, const float *ref,
+                      float ref_trace, float *out)
+{
+    const int A4 = A & ~3;
+    /* the centre's SoA form is shared by every frame */
+    float *rsoa = (float *)malloc((size_t)(A4 + 4) * 3 * sizeof(float));
+    for (int a = 0; a < A4; a += 4) {
+        __m128 x, y, z;
+        aos4_to_soa(ref + 3 * a, &x, &y, &z);
+        _mm_storeu_ps(rsoa + 3 * a, x);
+        _mm_storeu_ps(rsoa + 3 * a + 4, y);
+        _mm_storeu_ps(rsoa + 3 * a + 8, z);
+    }
+#pragma omp parallel for schedule(static)
+    for (long f = 0; f < n; ++f) {
+        const float *p = xyz + (size_t)f * A * 3;
+        __m128 acc[9];
+        for (int e = 0; e < 9; ++e) acc[e] = _mm_setzero_ps();
+        for (int a = 0; a < A4; a += 4) {
+            __m128 x[3], y[3];
+            aos4_to_soa(p + 3 * a, &x[0], &x[1], &x[2]);
+            y[0] = _mm_loadu_ps(rsoa + 3 * a);
+            y[1] = _mm_loadu_ps(rsoa + 3 * a + 4);
+            y[2] = _mm_loadu_ps(rsoa + 3 * a + 8);
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j)
+                    acc[3 * i + j] = _mm_add_ps(acc[3 * i + j], _mm_mul_ps(x[i], y[j]));
+        }
+        float Mf[9];
+        for (int e = 0; e < 9; ++e) Mf[e] = hsum4(acc[e]);
+        for (int a = A4; a < A; ++a) {
+            const float *x = p + 3 * a, *y = ref + 3 * a;
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) {
+                    const float prod = x[i] * y[j];
+                    Mf[3 * i + j] = Mf[3 * i + j] + prod;
+                }
+        }
+        double M[9];
+        for (int e = 0; e < 9; ++e) M[e] = Mf[e];
+        const double msd = qcp_msd(M, (double)traces32[f], (double)ref_trace, A);
+        out[f] = sqrtf((float)msd);
+    }
+    free(rsoa);
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* md.rmsd(traj, ref) exactly as the reference calls it (NOT precentered): copy + centre both */
 /* every call, then QCP.  This is what the reference pays per k-centers iteration (SURVEY.md  */
-/* 3.2), so it is what the CPU baseline times.  mode 0 = f64 truth, 1 = mdtraj-like float32.  */
+/* 3.2), so it is what the CPU baseline times.  mode 0 = f64 truth, 1 = mdtraj-like float32 (scalar lanes), 2 = the same with SSE. */
 /* ------------------------------------------------------------------------------------------ */
 int orc_md_rmsd(const float *xyz, long n, int A, const float *ref, int mode, float *out)
 {
@@ -224,8 +309,10 @@ int orc_md_rmsd(const float *xyz, long n, int A, const float *ref, int mode, flo
     orc_center_and_trace(rc, 1, A, &rt64, &rt32);
     if (mode == 0)
         orc_rmsd_f64(copy, t64, n, A, rc, rt64, out);
-    else
+    else if (mode == 1)
         orc_rmsd_f32(copy, t32, n, A, rc, rt32, out);
+    else
+        orc_rmsd_f32_sse(copy, t32, n, A, rc, rt32, out);
     free(copy); free(rc); free(t64); free(t32);
     return 0;
 }
@@ -320,6 +407,84 @@ long orc_kcenters_update_f32(const float *dist, long n, long center_id, double *
         }
     }
     return best;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* The synthetic-trajectory generator of enspara_b200/synth.py, restated in C   */
+/* so that the CPU arms of bench.py can make their host sample without numpy's minutes and     */
+/* without loading the product's CUDA library.  Integer hashing + separately rounded float32   */
+/* operations only (-ffp-contract=off): bit-identical to synth.trajectory (tested).            */
+/* ------------------------------------------------------------------------------------------ */
+static inline uint64_t syn_mix64(uint64_t z)
+{
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+static inline float syn_u01(uint64_t key, uint64_t idx, uint64_t counter)
+{
+    const uint64_t z = syn_mix64(key ^ syn_mix64(idx * 0xD1B54A32D192ED03ULL + counter));
+    return (float)(z >> 40) * 5.9604644775390625e-08f;
+}
+static inline float syn_gauss4(uint64_t key, uint64_t idx, uint64_t c)
+{
+    const float u0 = syn_u01(key, idx, c), u1 = syn_u01(key, idx, c + 1);
+    const float u2 = syn_u01(key, idx, c + 2), u3 = syn_u01(key, idx, c + 3);
+    const float s = (u0 + u1) + (u2 + u3);
+    return (s - 2.0f) * 1.7320508f;
+}
+
+void orc_synth_trajectory(float *out, long n, int A, long first_frame, uint64_t seed,
+                          const float *base, int n_base)
+{
+    const uint64_t key = syn_mix64(seed + 0x9E3779B97F4A7C15ULL * 2ULL); /* stream 1: frames */
+#pragma omp parallel for schedule(static)
+    for (long fl = 0; fl < n; ++fl) {
+        const uint64_t f = (uint64_t)(first_frame + fl);
+        const float sigma = 0.02f + 0.13f * syn_u01(key, f, 0);
+        const float q0 = syn_gauss4(key, f, 1), q1 = syn_gauss4(key, f, 5);
+        const float q2 = syn_gauss4(key, f, 9), q3 = syn_gauss4(key, f, 13);
+        float qn = sqrtf((q0 * q0 + q1 * q1) + (q2 * q2 + q3 * q3));
+        if (!(qn > 1e-6f)) qn = 1e-6f;
+        const float w = q0 / qn, x = q1 / qn, y = q2 / qn, z = q3 / qn;
+        const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z;
+        const float xw = x * w, yw = y * w, zw = z * w;
+        const float r00 = 1.0f - 2.0f * (yy + zz), r01 = 2.0f * (xy - zw), r02 = 2.0f * (xz + yw);
+        const float r10 = 2.0f * (xy + zw), r11 = 1.0f - 2.0f * (xx + zz), r12 = 2.0f * (yz - xw);
+        const float r20 = 2.0f * (xz - yw), r21 = 2.0f * (yz + xw), r22 = 1.0f - 2.0f * (xx + yy);
+        const float t0 = 2.0f * syn_u01(key, f, 17) - 1.0f;
+        const float t1 = 2.0f * syn_u01(key, f, 18) - 1.0f;
+        const float t2 = 2.0f * syn_u01(key, f, 19) - 1.0f;
+        const float *b = base + (size_t)(f % (uint64_t)n_base) * A * 3;
+        float *o = out + (size_t)fl * A * 3;
+        for (int a = 0; a < A; ++a) {
+            const uint64_t c0 = 32 + (uint64_t)(3 * a) * 4;
+            const float px = b[3 * a] + sigma * syn_gauss4(key, f, c0);
+            const float py = b[3 * a + 1] + sigma * syn_gauss4(key, f, c0 + 4);
+            const float pz = b[3 * a + 2] + sigma * syn_gauss4(key, f, c0 + 8);
+            o[3 * a] = ((r00 * px + r01 * py) + r02 * pz) + t0;
+            o[3 * a + 1] = ((r10 * px + r11 * py) + r12 * pz) + t1;
+            o[3 * a + 2] = ((r20 * px + r21 * py) + r22 * pz) + t2;
+        }
+    }
+}
+
+void orc_synth_features(float *X, long n, long F, long first_row, uint64_t seed)
+{
+    const uint64_t key = syn_mix64(seed + 0x9E3779B97F4A7C15ULL * 3ULL); /* stream 2: features */
+#pragma omp parallel for schedule(static)
+    for (long r = 0; r < n; ++r)
+        for (long j = 0; j < F; ++j)
+            X[r * F + j] = syn_u01(key, (uint64_t)(first_row + r), (uint64_t)j);
+}
+
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
 }
 
 int orc_num_threads(void)

@@ -1,0 +1,29 @@
+#!/bin/bash
+# compute-sanitizer passes over the hot path: memcheck / racecheck /
+# synccheck on one small invocation of every kernel family (smoke(): RMSD k-centers + PAM +
+# euclidean k-centers) and on the emulated multi-rank peer-memory exchange.  Writes
+# gpurun_out/sanitize_<tool>_<what>.log; the ERROR SUMMARY lines are what profiles/ keeps.
+set -u
+OUT=${1:-gpurun_out}
+mkdir -p "$OUT"
+CS=/usr/local/cuda/bin/compute-sanitizer
+export EB_EXCH_TIMEOUT_S=600
+for tool in memcheck racecheck synccheck; do
+  timeout 240 $CS --tool $tool --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" \
+      > "$OUT/sanitize_${tool}_smoke.log" 2>&1
+  echo "$tool smoke rc=$? : $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' "$OUT/sanitize_${tool}_smoke.log" | tail -1)"
+  timeout 240 $CS --tool $tool --print-limit 20 python -m pytest -q -x \
+      tests/test_gpu_exchange_single.py::test_overlapping_ranks_small_shards \
+      tests/test_gpu_exchange_single.py::test_empty_shards_and_stop_rule \
+      > "$OUT/sanitize_${tool}_exchange.log" 2>&1
+  echo "$tool exchange rc=$? : $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' "$OUT/sanitize_${tool}_exchange.log" | tail -1)"
+done
+# tensor-core screen + re-score (tcgen05 / TMEM / mbarrier ring) and the TMA step kernel
+timeout 240 $CS --tool memcheck --print-limit 20 python -m pytest -q -x \
+    "tests/test_gpu_tc_screen.py::test_tc_assign_equals_exact_assign" \
+    > "$OUT/sanitize_memcheck_tc.log" 2>&1
+echo "memcheck tc rc=$? : $(grep -E 'ERROR SUMMARY' "$OUT/sanitize_memcheck_tc.log" | tail -1)"
+timeout 240 $CS --tool racecheck --print-limit 20 python -m pytest -q -x \
+    "tests/test_gpu_tc_screen.py::test_tc_assign_equals_exact_assign" \
+    > "$OUT/sanitize_racecheck_tc.log" 2>&1
+echo "racecheck tc rc=$? : $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' "$OUT/sanitize_racecheck_tc.log" | tail -1)"

@@ -55,6 +55,75 @@ def main():
         [int(c) for c in serial.center_indices]
     ok &= np.array_equal(shard.assignments, serial.assignments[bounds[rank]:bounds[rank + 1]])
     ok &= np.array_equal(shard.distances, serial.distances[bounds[rank]:bounds[rank + 1]])
+    # ---- config-4-shaped shards (BASELINE configs[3]): >= 40k frames x 500 atoms per rank, so
+    # the kernel is k_kcenters_step_rmsd_tma and the exchange the fused peer-memory one -- the
+    # combination bench.py times at N > 1.  Sharded == single GPU on centres, assignments AND
+    # distances (the reference's MPI bar, test_cluster.py:270-275, 309-314), for a run bounded
+    # by n_clusters and for one terminated by dist_cutoff (kcenters.py:217).
+    from enspara_b200 import _lib
+    per = int(os.environ.get("EB_MGPU_C4_FRAMES", "100000"))
+    A = 500
+    full = synth.device_trajectory(per * size, A, seed=0, first_frame=0)
+    mine = synth.device_trajectory(per, A, seed=0, first_frame=rank * per)
+    lo, hi = rank * per, (rank + 1) * per
+    p2p_wanted = os.environ.get("ENSPARA_B200_P2P", "1") != "0"
+    report = {}
+
+    def same(shard, serial, tag):
+        g = [int(r * per + l) for r, l in shard.center_indices]
+        c = g == [int(v) for v in serial.center_indices]
+        a = np.array_equal(shard.assignments, serial.assignments[lo:hi])
+        d = np.array_equal(shard.distances, serial.distances[lo:hi])
+        report[tag] = dict(k=len(g), centres=bool(c), assignments=bool(a), distances=bool(d))
+        return c and a and d
+
+    serial = kcenters.kcenters(full, "rmsd", n_clusters=24, mpi_mode=False)
+    shard, eng = kcenters.kcenters(mine, "rmsd", n_clusters=24, mpi_mode=True,
+                                   _return_engine=True)
+    ok &= same(shard, serial, "c4_n_clusters")
+    ok &= bool(_lib.load().eb_kcenters_step_rmsd_uses_tma(per, A))
+    ok &= (eng.p2p == p2p_wanted)
+    report["c4_kernel_is_tma"] = bool(_lib.load().eb_kcenters_step_rmsd_uses_tma(per, A))
+    report["c4_exchange_is_fused_p2p"] = bool(eng.p2p)
+    report["c4_wait_us_per_step"] = 1e-3 * getattr(eng, "wait_ns", 0) / 24
+    # cutoff-terminated: a radius between the 17th and the 24th centre's max-min-distance, so
+    # the stop rule (not n_clusters) ends the run, after several polls of the device state
+    cut = float(serial.distances.max()) * 1.03
+    serial_c = kcenters.kcenters(full, "rmsd", dist_cutoff=cut, mpi_mode=False)
+    shard_c = kcenters.kcenters(mine, "rmsd", dist_cutoff=cut, mpi_mode=True)
+    ok &= same(shard_c, serial_c, "c4_dist_cutoff")
+    ok &= 1 < len(serial_c.center_indices) <= 24
+    ok &= float(serial_c.distances.max()) <= cut
+    # both bounds at once, and the exchange buffer re-used by a third run in a row
+    serial_b = kcenters.kcenters(full, "rmsd", n_clusters=7, dist_cutoff=cut, mpi_mode=False)
+    shard_b = kcenters.kcenters(mine, "rmsd", n_clusters=7, dist_cutoff=cut, mpi_mode=True)
+    ok &= same(shard_b, serial_b, "c4_both")
+    del full, mine, serial, shard, eng, serial_c, shard_c, serial_b, shard_b
+    torch.cuda.empty_cache()
+
+    # ---- k-hybrid WITHOUT a seed (random_state=None): every rank's global RandomState is
+    # seeded differently; the sweep must still consume ONE stream (rank 0's), or ranks pick
+    # different owners / broadcast roots and hang or diverge (the reference: rank 0 draws,
+    # mpi/ops.py:247-253)
+    np.random.seed(1000 + rank)
+    X = synth.trajectory(1500, 30, seed=13)
+    bounds = np.linspace(0, len(X), size + 1).astype(int)
+    un = hybrid.hybrid(X[bounds[rank]:bounds[rank + 1]], "rmsd", n_clusters=9, n_iters=2,
+                       random_state=None, mpi_mode=True)
+    mine_ids = torch.tensor([int(bounds[r] + l) for r, l in un.center_indices],
+                            dtype=torch.int64, device="cuda")
+    every = [torch.empty_like(mine_ids) for _ in range(size)]
+    dist.all_gather(every, mine_ids)
+    ok &= all(bool(torch.equal(e, every[0])) for e in every)
+    # ... and the state is self-consistent: every frame sits with its nearest medoid
+    from enspara_b200.cluster import util as cutil
+    med = [X[int(g)] for g in every[0].cpu().numpy()]
+    a2, d2 = cutil.assign_to_nearest_center(X[bounds[rank]:bounds[rank + 1]], med, "rmsd")
+    ok &= np.array_equal(a2, un.assignments)
+    ok &= np.allclose(d2, un.distances, rtol=1e-6, atol=1e-7)
+    report["khybrid_unseeded_ranks_agree"] = bool(
+        all(bool(torch.equal(e, every[0])) for e in every))
+
     # the `cluster` app under torchrun: file i on rank i % size, results re-assembled on every
     # rank, rank 0 writes -- must equal the serial estimator (test_apps_cluster_mpi.py:100-139)
     import tempfile
@@ -92,6 +161,10 @@ def main():
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
+        import json
+        report["ranks"] = size
+        report["ok"] = bool(int(flag.item()) == 1)
+        print("MGPU_REPORT " + json.dumps(report), flush=True)
         print("MGPU_OK" if int(flag.item()) == 1 else "MGPU_FAIL", flush=True)
     dist.barrier()
     dist.destroy_process_group()

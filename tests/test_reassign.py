@@ -24,6 +24,15 @@ def test_compute_batches_follows_the_reference_rule():
     assert rz.compute_batches([12], 10) == [[], [0]]
 
 
+def test_first_file_filling_a_batch_leaves_no_empty_batch():
+    # lengths[0] >= batch_size: compute_batches opens with [] (reference rule); the streaming
+    # pass must not see it (it chains a prefetch from every batch to the next)
+    assert rz.compute_batches([100, 10, 20], 100) == [[], [0], [1, 2]]
+    assert rz.nonempty_batches([100, 10, 20], 100) == [[0], [1, 2]]
+    assert rz.nonempty_batches([], 10) == []
+    assert rz.nonempty_batches([5, 5, 5], 11) == [[0, 1], [2]]
+
+
 def test_sound_and_load(tmp_path, frame0_h5_xyz):
     from enspara_b200.util import h5min
     p_npy = str(tmp_path / "a.npy")
@@ -112,6 +121,15 @@ def test_reassign_streams_files_and_matches_oracle(tmp_path, frame0_xyz, monkeyp
                               ["all"], centers)
     assert isinstance(assig, np.ndarray) and assig.shape == (2, 100)
     assert_array_equal(assig.reshape(-1), ea[:200])
+
+    # the first file exactly fills a batch (lengths[0] == batch_size; the case that used to
+    # leave the prefetch chain without a head)
+    first_big = [files[2], files[0], files[1]]          # 179, 120, 1 frames
+    monkeypatch.setattr(rz, "determine_batch_size", lambda *a, **k: (179, 0.0))
+    l2 = [rz.sound_trajectory(f) for f in first_big]
+    a2, d2 = rz.batch_reassign([(f, None, None) for f in first_big], centers, l2, 0.5)
+    assert [len(a) for a in a2] == l2
+    assert_array_equal(np.concatenate(a2), np.concatenate([ea[121:300], ea[:120], ea[120:121]]))
 
     with pytest.raises(ImproperlyConfigured):          # batch smaller than the largest file
         monkeypatch.setattr(rz, "determine_batch_size", lambda *a, **k: (100, 0.0))
