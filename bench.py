@@ -221,7 +221,7 @@ def _checksum(center_list, assign, dist, first_index):
     return s, c
 
 
-def sharded_parity_check(world, rank, A, per_rank=40_000, n_centers=12):
+def sharded_parity_check(world, rank, A, per_rank=80_000, n_centers=12):
     """Untimed.  A down-scaled copy of the bench's global trajectory (per_rank frames per rank,
     still large enough for the TMA step kernel + the exchange that the timed steps use) is
     clustered twice through the public function: sharded over the N ranks, and in one piece on

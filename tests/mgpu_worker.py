@@ -55,7 +55,7 @@ def main():
         [int(c) for c in serial.center_indices]
     ok &= np.array_equal(shard.assignments, serial.assignments[bounds[rank]:bounds[rank + 1]])
     ok &= np.array_equal(shard.distances, serial.distances[bounds[rank]:bounds[rank + 1]])
-    # ---- config-4-shaped shards (BASELINE configs[3]): >= 40k frames x 500 atoms per rank, so
+    # ---- config-4-shaped shards (BASELINE configs[3]): >= 76k frames x 500 atoms per rank, so
     # the kernel is k_kcenters_step_rmsd_tma and the exchange the fused peer-memory one -- the
     # combination bench.py times at N > 1.  Sharded == single GPU on centres, assignments AND
     # distances (the reference's MPI bar, test_cluster.py:270-275, 309-314), for a run bounded

@@ -139,10 +139,10 @@ def test_empty_shards_and_stop_rule(cuda):
 
 
 def test_tma_step_kernel_with_exchange(cuda):
-    """Config-4-shaped shards (500 atoms, >= 37 888 frames per rank): the step kernel is
+    """Config-4-shaped shards (500 atoms, >= 75 776 frames per rank): the step kernel is
     k_kcenters_step_rmsd_tma, one CTA per SM -- the combination bench.py times at N > 1."""
     from enspara_b200 import _lib
-    per = 40_000
+    per = 80_000
     assert _lib.load().eb_kcenters_step_rmsd_uses_tma(per, 500)
     bounds = np.array([0, per, 2 * per])
     _check(cuda, 2 * per, 500, bounds, n_clusters=10, cutoff=0.0, lockstep=True, seed=0)
