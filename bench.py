@@ -317,6 +317,7 @@ def run_b200(args):
         time.sleep(0.3)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     barrier()
+    wait_ns_before = int(eng.read_state().wait_ns)   # warm-up incl. the ranks' start-up skew
     t0 = time.perf_counter()
     ev[0].record()
     for i in range(K):
@@ -341,9 +342,9 @@ def run_b200(args):
 
     exch_wait_us = None
     if world > 1 and eng.p2p:
-        # time block 0 spent in the prologue waiting for the peers' records, per step since
-        # the seed (the spread between the GPUs: every iteration waits for the slowest shard)
-        exch_wait_us = 1e-3 * float(st.wait_ns) / max(1, K + W)
+        # time block 0 spent in the prologue waiting for the peers' records, per TIMED step
+        # (the spread between the GPUs: every iteration waits for the slowest shard)
+        exch_wait_us = 1e-3 * float(int(st.wait_ns) - wait_ns_before) / max(1, K)
 
     parity = None
     if world > 1 and not args.no_parity_check:
