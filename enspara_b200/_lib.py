@@ -68,6 +68,8 @@ SIGNATURES = {
     "eb_tc_scratch_bytes": (_sz, [_i64, _int, _i32]),
     "eb_rmsd_assign_tc": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _i32, _dbl, _vp, _int, _vp, _vp,
                                  _vp, _vp, _vp, _int, _vp]),
+    "eb_rmsd_score_lists": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp,
+                                   _vp, _vp, _vp, _vp, _vp]),
     "eb_feat_assign": (_int, [_vp, _i64, _i64, _int, _int, _vp, _i32, _vp, _i64, _vp, _vp,
                               _int, _int, _vp]),
     "eb_pam_classify": (_int, [_vp, _vp, _vp, _i64, _int, _i32, _vp, _vp, _vp, _vp, _vp]),

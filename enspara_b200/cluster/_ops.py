@@ -134,14 +134,98 @@ def assign_device(metric, data, centers, frame_idx=None, out_dist=None, out_assi
 TC_MIN_CENTERS = 64
 #: frames per screen pass (bounds the split-operand scratch: 2 x 12*A_pad bytes per frame)
 TC_CHUNK_FRAMES = 262144
-#: error model of the 3xTF32 screen: |N * d(msd)| <= TC_KAPPA_PER_ATOM * A_pad * sqrt(Ga*Gb).
-#: Measured on B200 (scripts/dev_tc_debug.py): the worst pair is 1.0 * 2^-24 per atom (FP32
-#: accumulation in the tensor core truncates); 8x margin.
-TC_KAPPA_PER_ATOM = 8.0 * 2.0 ** -24
+#: Error model of the split-FP16 screen: |delta(N * msd)| <= kappa * sqrt(Ga * Gb) with
+#: kappa = TC_KAPPA_PER_ATOM * A_pad + TC_KAPPA_CONST.  Derivation (DESIGN.md "K3t error bound"):
+#: * entry (i, j) of M is the FP32 sum of 3 * A products (h1 g1, h1 g2, h2 g1 per atom).  Every
+#:   addend entering the accumulator (3 * A products + 3 * A / 16 instruction-level accumulate
+#:   steps = 3.19 A) is charged ONE truncation of relative size u = 2^-23 of a quantity bounded by
+#:   B_ij = sum_a |x_ia| |y_ja| (every partial sum is): |dM_ij| <= 3.19 A u B_ij;
+#: * representation: |x - (h1 + h2) / 2^8| <= 2^-24 |x| (+ 2^-33 nm absolute once h2 is
+#:   subnormal), dropped h2 g2 <= 2^-22 |x| |y|: together < 3 u B_ij (the constant term);
+#: * Cauchy-Schwarz: B_ij <= sqrt(Gx_i Gy_j), hence ||dM||_F <= (3.19 A + 3) u sqrt(Ga Gb);
+#: * lambda_max = max over rotations R of tr(R^T M) (Horn), so |d lambda| <= ||dM||_* <=
+#:   sqrt(3) ||dM||_F, and N * msd = Ga + Gb - 2 lambda doubles it.
+#: Measured worst case on B200 (tests/test_gpu_tc_screen.py::test_tc_error_bound): ~1/20 of this
+#: bound.  Round 1 used 8 * 2^-24 per atom, 8x the measurement but not a bound.
+TC_KAPPA_PER_ATOM = 2.0 * 3.0 ** 0.5 * 3.19 * 2.0 ** -23
+TC_KAPPA_CONST = 2.0 * 3.0 ** 0.5 * 3.0 * 2.0 ** -23
+
+
+def tc_kappa(a_pad):
+    return TC_KAPPA_PER_ATOM * a_pad + TC_KAPPA_CONST
+
+
+#: Built-in audit of the screen (ENSPARA_B200_TC_AUDIT: 0 off, 1 default, 2 every call): a random
+#: sample of the frames of a pass is scored against ALL centres with the exact float64 kernel
+#: and must reproduce the distance and the assignment the screen + re-score produced, bit for
+#: bit; a mismatch raises.  Dense passes (>= TC_AUDIT_MIN_PAIRS frame-centre pairs) are always
+#: audited; small passes (PAM's per-proposal subsets) once every TC_AUDIT_EVERY calls.
+TC_AUDIT_FRAMES = 64
+TC_AUDIT_MIN_PAIRS = 1 << 24
+TC_AUDIT_EVERY = 64
+TC_AUDIT_LIST = 256
+_audit_calls = [0]
+audit_stats = {"passes_audited": 0, "frames_audited": 0}
+
+
+def _audit_level():
+    import os
+    return int(os.environ.get("ENSPARA_B200_TC_AUDIT", "1"))
+
+
+def _audit_tc(data, centers, k, m, frame_idx, scatter, out_dist, out_assign, ws):
+    """Exact-score a sample of the pass's frames against every centre and compare."""
+    dev = data.xyz.device
+    S = min(TC_AUDIT_FRAMES, m)
+    L = TC_AUDIT_LIST
+    chunks = (k + L - 1) // L
+    key = ("audit", k, S)
+    if ws.get("audit_key") != key:
+        ch = torch.arange(chunks, device=dev, dtype=torch.int32)
+        lists = (ch[:, None] * L + torch.arange(L, device=dev, dtype=torch.int32)[None, :])
+        ws["audit_lists"] = lists.repeat(S, 1).contiguous()                    # (S*chunks, L)
+        ws["audit_count"] = torch.clamp(k - ch * L, max=L).to(torch.int32).repeat(S).contiguous()
+        ws["audit_lo"] = torch.full((S * chunks * L,), float("-inf"), dtype=torch.float32,
+                                    device=dev)
+        ws["audit_up"] = torch.full((S * chunks,), float("inf"), dtype=torch.float32, device=dev)
+        ws["audit_zero"] = torch.zeros(4, dtype=torch.int32, device=dev)
+        ws["audit_d"] = torch.empty(S * chunks, dtype=torch.float32, device=dev)
+        ws["audit_a"] = torch.empty(S * chunks, dtype=torch.int32, device=dev)
+        ws["audit_flag"] = torch.empty(S * chunks, dtype=torch.int32, device=dev)
+        ws["audit_gen"] = torch.Generator(device=dev)
+        ws["audit_gen"].manual_seed(0x5EED)
+        ws["audit_key"] = key
+    pos = torch.randint(0, m, (S,), device=dev, generator=ws["audit_gen"])
+    src = pos if frame_idx is None else frame_idx[:m][pos]
+    res = src if (scatter and frame_idx is not None) else pos
+    fidx = src.to(torch.int64).repeat_interleave(chunks).contiguous()
+    _lib.call("eb_rmsd_score_lists", ptr(data.xyz), ptr(data.traces), S * chunks, data.n_atoms,
+              ptr(centers.xyz), ptr(centers.traces), ptr(ws["audit_count"]),
+              ptr(ws["audit_lists"]), L, ptr(ws["audit_lo"]), ptr(ws["audit_up"]),
+              ptr(ws["audit_zero"]), ptr(fidx), ptr(ws["audit_d"]), ptr(ws["audit_a"]),
+              ptr(ws["audit_flag"]), stream_ptr())
+    # nearest over the chunks, lowest centre index on ties: (distance bits, index) as one key
+    keyv = (ws["audit_d"].view(torch.int32).to(torch.int64) << 32) | ws["audit_a"].to(torch.int64)
+    best = keyv.view(S, chunks).min(dim=1).values
+    want_d = (best >> 32).to(torch.int32).view(torch.float32)
+    want_a = (best & 0xFFFFFFFF).to(torch.int32)
+    bad = (want_d != out_dist[res]) | (want_a != out_assign[res])
+    audit_stats["passes_audited"] += 1
+    audit_stats["frames_audited"] += S
+    if bool(bad.any().item()):
+        i = int(torch.nonzero(bad)[0])
+        raise RuntimeError(
+            "enspara_b200: tensor-core screen audit FAILED for frame %d: screen path gave "
+            "(centre %d, %.9g nm), exact path (centre %d, %.9g nm).  Set "
+            "ENSPARA_B200_TC_MIN_CENTERS to a huge value to force the exact kernel and please "
+            "report this." % (int(src[i]), int(out_assign[res][i]), float(out_dist[res][i]),
+                              int(want_a[i]), float(want_d[i])))
 
 
 def tc_applicable(metric, data, k):
-    return metric.is_rmsd and k >= TC_MIN_CENTERS and len(data) >= 1
+    import os
+    min_k = int(os.environ.get("ENSPARA_B200_TC_MIN_CENTERS", TC_MIN_CENTERS))
+    return metric.is_rmsd and k >= min_k and len(data) >= 1
 
 
 def assign_device_tc(metric, data, centers, k=None, stats=None, frame_idx=None, n_idx=None,
@@ -171,7 +255,7 @@ def assign_device_tc(metric, data, centers, k=None, stats=None, frame_idx=None, 
     if ws.get("cand") is None or ws["cand"].numel() < m:
         ws["cand"] = torch.empty(m + m // 4 + 128, dtype=torch.int32, device=dev)
     scratch, cand = ws["scratch"], ws["cand"][:m]
-    kappa = TC_KAPPA_PER_ATOM * data.a_pad
+    kappa = tc_kappa(data.a_pad)
     for lo in range(0, m, chunk):
         hi = min(m, lo + chunk)
         if frame_idx is None:
@@ -205,6 +289,12 @@ def assign_device_tc(metric, data, centers, k=None, stats=None, frame_idx=None, 
                                    frame_idx=frame_idx[:m][overflow].contiguous(), k=k)
             out_dist[overflow] = d2
             out_assign[overflow] = a2
+    level = _audit_level()
+    if level > 0:
+        _audit_calls[0] += 1
+        if (level >= 2 or m * k >= TC_AUDIT_MIN_PAIRS
+                or _audit_calls[0] % TC_AUDIT_EVERY == 0):
+            _audit_tc(data, centers, k, m, frame_idx, scatter, out_dist, out_assign, ws)
     return out_dist, out_assign
 
 

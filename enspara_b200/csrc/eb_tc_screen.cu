@@ -1,4 +1,4 @@
-// K3 on the tensor cores: many-centres RMSD as 3xTF32 tcgen05 GEMMs with a fused QCP epilogue
+// K3 on the tensor cores: many-centres RMSD as split-FP16 tcgen05 GEMMs with a fused QCP epilogue
 // ("screen"), followed by exact float64 re-scoring of the few centres per frame that survive.
 //
 // Reference behaviour reproduced: cluster/util.py:159-205 (assign_to_nearest_center) -- the
@@ -11,15 +11,25 @@
 // is a plain (frames x atoms) . (atoms x 3*centres) GEMM; the three D_i share the B operand and
 // put all nine entries of M(f,c) into ONE thread of the epilogue (TMEM lane f holds row f of
 // D_0, D_1, D_2), so the 3x3 matrix is never exchanged between threads or written to memory.
-// TF32 has 10 mantissa bits, so every operand is split x = hi + lo (hi = x truncated to TF32,
-// lo = x - hi, exact) and D = Ahi.Bhi + Ahi.Blo + Alo.Bhi is accumulated in FP32 in TMEM
-// (3xTF32).  Operands are pre-split AND pre-packed by k_pack_tf32 into the exact swizzled
-// shared-memory image of every tile (64-byte rows, SWIZZLE_64B), so one pipeline stage arrives
-// with two contiguous bulk copies (cp.async.bulk) in a 3-stage mbarrier ring; one elected thread issues
-// tcgen05.mma.kind::tf32 (M=128 frames, N=144 = 48 centres x 3), 9 MMAs per 8 atoms.
+// Operand precision: every coordinate is scaled by 2^8 and split into TWO FP16 numbers,
+// x*256 = h1 + h2 with h1 = rn_fp16(x*256), h2 = rn_fp16(x*256 - h1).  Round-to-nearest keeps
+// 11 + 11 significant bits plus the sign of h2, i.e. |x*256 - h1 - h2| <= 2^-24 |x*256| (FP32
+// input precision) as long as h2 is a normal FP16 number and an absolute 2^-25 otherwise, and
+// D = A1.B1 + A1.B2 + A2.B1 is accumulated in FP32 in TMEM (the dropped A2.B2 term is 2^-24
+// relative).  Compared with the 3xTF32 split of round 1 (hi/lo FP32 words: 8 bytes per element,
+// 8 atoms per MMA) this is 4 bytes per element and 16 atoms per MMA at the same cycles per
+// dispatch: half the operand traffic and half the tensor time for the same accuracy class --
+// the error that matters is the FP32 accumulation inside the tensor core (see TC_KAPPA in
+// cluster/_ops.py).  Coordinates beyond +-255 nm would overflow FP16: the pack kernel raises
+// a flag and the whole pass falls back to the exact kernel.  Operands are pre-split AND
+// pre-packed by k_pack_f16x2 into the exact swizzled shared-memory image of every tile
+// (64-byte rows = 32 atoms, SWIZZLE_64B), so one pipeline stage arrives with two contiguous
+// bulk copies (cp.async.bulk) in a 3-stage mbarrier ring; one elected thread issues
+// tcgen05.mma.kind::f16 (M=128 frames, N=144 = 48 centres x 3), 9 MMAs per 16 atoms.
 //
 // Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2-5
 // epilogue (TMEM lane quarter = warp_id % 4).
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "eb_rmsd.cuh"
@@ -31,11 +41,14 @@ namespace tc {
 constexpr int BM = 128;                  // frames per tile  (= TMEM lanes)
 constexpr int NC = 48;                   // centres per tile
 constexpr int BN = 3 * NC;               // B rows per tile: (centre, coordinate)
-constexpr int BK = 16;                   // atoms per stage: 64-byte rows
+constexpr int BK = 32;                   // atoms per stage: 64-byte rows of FP16
 constexpr int STAGES = 3;
-constexpr int A_TILE = BM * BK * 4;      // 8192
-constexpr int B_TILE = BN * BK * 4;      // 6144
-constexpr int STAGE_BYTES = 6 * A_TILE + 2 * B_TILE;  // {hi,lo} x 3 coords of A, {hi,lo} of B
+constexpr int A_TILE = BM * BK * 2;      // 8192
+constexpr int B_TILE = BN * BK * 2;      // 9216
+constexpr int STAGE_BYTES = 6 * A_TILE + 2 * B_TILE;  // {h1,h2} x 3 coords of A, {h1,h2} of B
+constexpr float kOperandScale = 256.0f;               // x*2^8 before the FP16 split
+constexpr float kAccumUnscale = 1.0f / 65536.0f;      // accumulators hold 2^16 * M
+constexpr float kF16Limit = 65000.0f;                 // |x*2^8| beyond this cannot be split
 constexpr int TMEM_COLS = 512;           // 3 accumulators x 144 columns = 432 -> power of two
 constexpr int THREADS = 64 + 128 * 2;  // producer, MMA, 8 epilogue warps
 constexpr int CAND_BUDGET = 512;  // candidate entries per frame, shared out over its lists
@@ -49,23 +62,34 @@ static_assert(3 * BN <= TMEM_COLS, "three accumulators must fit TMEM");
 static_assert(BN % 16 == 0 && BN <= 256, "UMMA N constraint for M = 128");
 
 // ---- operand split + packing -----------------------------------------------------------------
-// Writes, for every (tile T, k-block kb, sub-row-set s, hi|lo), the exact shared-memory image of
-// the MMA operand tile (RT rows x 64 bytes, SWIZZLE_64B: 16-byte chunk c of row r lives at chunk
-// c ^ ((r >> 1) & 3)), contiguously in global memory, so that a whole pipeline stage arrives
-// with ONE bulk copy instead of hundreds of 64-byte TMA row requests.
+// Writes, for every (tile T, k-block kb, sub-row-set s, h1|h2), the exact shared-memory image of
+// the MMA operand tile (RT rows x 64 bytes = 32 FP16 atoms, SWIZZLE_64B: 16-byte chunk c of row
+// r lives at chunk c ^ ((r >> 1) & 3)), contiguously in global memory, so that a whole pipeline
+// stage arrives with ONE bulk copy instead of hundreds of 64-byte TMA row requests.
 //   image index = (((T * KB + kb) * S + s) * 2 + hl) * (RT * 64 bytes)
 //   source row  = (T * RT + r) * S + s   of the (rows_total x A_pad) float matrix `x`
 // Frames: RT = 128, S = 3 (the three coordinate rows of a frame); centres: RT = 144, S = 1.
 // `row_idx` (optional, frames only): tile row (T*RT + r) is frame row_idx[T*RT + r] of `x`.
-__global__ void __launch_bounds__(256)
-k_pack_tf32(const float *__restrict__ x, long rows_total, int A_pad, int RT, int S, long n_tiles,
-            const int64_t *__restrict__ row_idx, unsigned char *__restrict__ img)
+// One thread = one 16-byte chunk = 8 atoms.  *overflow is set when a coordinate cannot be
+// represented (|x| * 2^8 beyond the FP16 range): the caller then uses the exact kernel.
+__device__ __forceinline__ void split_f16x2(float x, __half &h1, __half &h2, bool &bad)
 {
-    const int Qs = A_pad >> 2;               // float4 per source row
-    const int KB = (A_pad + BK - 1) / BK;    // k-blocks of the image (zero-padded to 16 atoms)
-    const int Q = KB * (BK / 4);             // float4 per image row
+    const float v = x * kOperandScale;             // exact (power of two)
+    bad |= !(fabsf(v) <= kF16Limit);               // also catches NaN
+    h1 = __float2half_rn(v);
+    h2 = __float2half_rn(v - __half2float(h1));    // the difference is exact in FP32
+}
+
+__global__ void __launch_bounds__(256)
+k_pack_f16x2(const float *__restrict__ x, long rows_total, int A_pad, int RT, int S, long n_tiles,
+             const int64_t *__restrict__ row_idx, unsigned char *__restrict__ img, int *overflow)
+{
+    const int Qs = A_pad >> 3;               // 8-atom chunks per source row (A_pad % 8 == 0)
+    const int KB = (A_pad + BK - 1) / BK;    // k-blocks of the image (zero-padded to 32 atoms)
+    const int Q = KB * 4;                    // 16-byte chunks per image row
     const long total = n_tiles * RT * S * (long)Q;
     const size_t tile_bytes = (size_t)RT * 64;
+    bool bad = false;
     for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (long)gridDim.x * blockDim.x) {
         const int q = (int)(t % Q);
@@ -74,23 +98,24 @@ k_pack_tf32(const float *__restrict__ x, long rows_total, int A_pad, int RT, int
         const long tr = rr / S;          // T*RT + r
         const long T = tr / RT;
         const int r = (int)(tr - T * RT);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
         if (rr < rows_total && q < Qs) {
             const long src = row_idx ? (long)__ldg(row_idx + tr) * S + sidx : rr;
-            v = __ldg(reinterpret_cast<const float4 *>(x + (size_t)src * A_pad) + q);
+            const float4 *p = reinterpret_cast<const float4 *>(x + (size_t)src * A_pad) + 2 * q;
+            v0 = __ldg(p);
+            v1 = __ldg(p + 1);
         }
-        float4 h, l;
-        h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-        h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-        h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-        h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-        l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+        const float in[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        __align__(16) __half h1[8], h2[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) split_f16x2(in[e], h1[e], h2[e], bad);
         const int kb = q >> 2, c = q & 3;
         const size_t base = ((((size_t)T * KB + kb) * S + sidx) * 2) * tile_bytes +
                             (size_t)r * 64 + (size_t)((c ^ ((r >> 1) & 3)) << 4);
-        *reinterpret_cast<float4 *>(img + base) = h;
-        *reinterpret_cast<float4 *>(img + base + tile_bytes) = l;
+        *reinterpret_cast<uint4 *>(img + base) = *reinterpret_cast<const uint4 *>(h1);
+        *reinterpret_cast<uint4 *>(img + base + tile_bytes) = *reinterpret_cast<const uint4 *>(h2);
     }
+    if (bad) atomicOr(overflow, 1);
 }
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
@@ -102,12 +127,12 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar)
                      smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
-                                            uint32_t idesc, uint32_t accumulate)
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                           uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
         "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
@@ -136,8 +161,8 @@ __device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t saddr)
     return d;
 }
 constexpr uint32_t kIdesc = (1u << 4)          // D format F32
-                            | (2u << 7)        // A format TF32
-                            | (2u << 10)       // B format TF32
+                            | (0u << 7)        // A format F16
+                            | (0u << 10)       // B format F16
                             | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 
@@ -288,17 +313,17 @@ k_tc_screen(const unsigned char *__restrict__ a_img, const unsigned char *__rest
                         const uint64_t bhi = smem_desc_sw64(st + 6 * A_TILE);
                         const uint64_t blo = smem_desc_sw64(st + 6 * A_TILE + B_TILE);
 #pragma unroll
-                        for (int ks = 0; ks < BK / 8; ++ks) {
-                            const uint64_t koff = (uint64_t)((ks * 32) >> 4);  // 8 tf32 = 32 B
+                        for (int ks = 0; ks < BK / 16; ++ks) {
+                            const uint64_t koff = (uint64_t)((ks * 32) >> 4);  // 16 f16 = 32 B
 #pragma unroll
                             for (int i = 0; i < 3; ++i) {
                                 const uint64_t ahi = smem_desc_sw64(st + (2 * i) * A_TILE);
                                 const uint64_t alo = smem_desc_sw64(st + (2 * i + 1) * A_TILE);
                                 const uint32_t d = tmem_base + (uint32_t)(i * BN);
                                 const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
-                                tc_mma_tf32(d, ahi + koff, bhi + koff, kIdesc, first);
-                                tc_mma_tf32(d, ahi + koff, blo + koff, kIdesc, 1u);
-                                tc_mma_tf32(d, alo + koff, bhi + koff, kIdesc, 1u);
+                                tc_mma_f16(d, ahi + koff, bhi + koff, kIdesc, first);
+                                tc_mma_f16(d, ahi + koff, blo + koff, kIdesc, 1u);
+                                tc_mma_f16(d, alo + koff, bhi + koff, kIdesc, 1u);
                             }
                         }
                         tc_commit(&sm->empty[stage]);  // smem slot reusable once these MMAs retire
@@ -369,7 +394,8 @@ k_tc_screen(const unsigned char *__restrict__ a_img, const unsigned char *__rest
 #pragma unroll
                             for (int i = 0; i < 3; ++i)
 #pragma unroll
-                                for (int j = 0; j < 3; ++j) o[3 * i + j] = m[i][3 * cc + j];
+                                for (int j = 0; j < 3; ++j)
+                                    o[3 * i + j] = m[i][3 * cc + j] * kAccumUnscale;
                         }
                     }
 #pragma unroll
@@ -383,11 +409,13 @@ k_tc_screen(const unsigned char *__restrict__ a_img, const unsigned char *__rest
                             Gb[p] = __ldg(ctraces + c);
                             scf[p] = fmaxf(sa * sqrtf((float)Gb[p]), 1e-30f);
                             const float inv = __frcp_rn(scf[p]);
+                            const float inv_acc = inv * kAccumUnscale;   // accumulators: 2^16 M
                             gq[p] = (float)(0.5 * (Ga + Gb[p])) * inv;
 #pragma unroll
                             for (int i = 0; i < 3; ++i)
 #pragma unroll
-                                for (int j = 0; j < 3; ++j) Mn[p][3 * i + j] = m[i][3 * cc + j] * inv;
+                                for (int j = 0; j < 3; ++j)
+                                    Mn[p][3 * i + j] = m[i][3 * cc + j] * inv_acc;
                         }
                         qcp4_f32(Mn, gq, lam, dl);
 #pragma unroll
@@ -490,7 +518,8 @@ k_rescore(const float *__restrict__ xyz, const double *__restrict__ traces, long
           const int *__restrict__ cand_count, const int *__restrict__ cand_list,
           const float *__restrict__ cand_bound, const float *__restrict__ cand_umin, int n_seg,
           float *out_dist, int *out_assign, int *frame_flag,
-          const int64_t *__restrict__ frame_idx, int scatter, int MAX_CAND)
+          const int64_t *__restrict__ frame_idx, int scatter, int MAX_CAND,
+          const int *__restrict__ f16_overflow)
 {
     extern __shared__ __align__(16) unsigned char rs_smem[];
     const int list_cap = n_seg * MAX_CAND;
@@ -519,7 +548,8 @@ k_rescore(const float *__restrict__ xyz, const double *__restrict__ traces, long
             U = fminf(U, __shfl_xor_sync(0xffffffffu, U, msk));
             ovf |= __shfl_xor_sync(0xffffffffu, ovf, msk);
         }
-        const bool overflow = ovf != 0;
+        // a coordinate outside the FP16 split's range voids the whole screen: exact fallback
+        const bool overflow = ovf != 0 || __ldg(f16_overflow) != 0;
         const long src = valid ? (frame_idx ? (long)frame_idx[f] : f) : 0;  // row of xyz / traces
         const float4 *px = reinterpret_cast<const float4 *>(xyz + (size_t)src * stride);
         // compact the survivors of all lists into cl[0 .. cnt_g)
@@ -645,16 +675,23 @@ static int tc_pick_nseg(long n_ft, int n_ct)
 
 extern "C" {
 
+// bytes of the packed operand images per tile row (one frame: 3 coordinate rows; one centre:
+// 3 rows too): {h1, h2} x 2 bytes x 3 x A_img
+static size_t tc_img_row_bytes(int n_atoms)
+{
+    const int A_img = (rmsd_apad(n_atoms) + tc::BK - 1) / tc::BK * tc::BK;
+    return 2 * sizeof(__half) * 3 * (size_t)A_img;
+}
+
 size_t eb_tc_scratch_bytes(int64_t n, int n_atoms, int32_t k)
 {
-    const size_t row = sizeof(float) * 3 *
-                       (size_t)((rmsd_apad(n_atoms) + tc::BK - 1) / tc::BK * tc::BK);
+    const size_t row = tc_img_row_bytes(n_atoms);
     const long n_ft = (n + tc::BM - 1) / tc::BM;
     const int n_ct = (k + tc::NC - 1) / tc::NC;
     const size_t n_lists = (size_t)tc_pick_nseg(n_ft < 1 ? 1 : n_ft, n_ct < 1 ? 1 : n_ct) *
                            tc::EPI_HALVES;
-    // split copies of frames and centres + candidate lists
-    return 2 * row * (size_t)(n + tc::BM) + 2 * row * (size_t)(k + tc::NC) +
+    // split copies of frames and centres + candidate lists + flags
+    return row * (size_t)(n + tc::BM) + row * (size_t)(k + tc::NC) +
            (size_t)n * n_lists *
                (sizeof(int) + sizeof(float) +
                 tc_max_cand((int)n_lists) * (sizeof(int) + sizeof(float))) +
@@ -681,14 +718,14 @@ int eb_rmsd_assign_tc(const float *xyz_soa, const double *traces, int64_t n, int
     EB_CHECK_ARG(n < (1L << 31) / 3, "rmsd_assign_tc: too many frames for one pass");
     cudaStream_t s = (cudaStream_t)stream;
     const int A_pad = rmsd_apad(n_atoms);
-    const int A_img = (A_pad + tc::BK - 1) / tc::BK * tc::BK;   // image rows padded to 16 atoms
-    const size_t row = 3 * (size_t)A_img;  // floats per frame in the packed images
+    const int A_img = (A_pad + tc::BK - 1) / tc::BK * tc::BK;   // image rows padded to 32 atoms
+    const size_t row = tc_img_row_bytes(n_atoms);  // image bytes per frame / per centre
     // packed operand images (tile-padded): frames then centres
     const size_t a_rows = (size_t)((n + tc::BM - 1) / tc::BM) * tc::BM;   // frames, padded
     const size_t c_rows = (size_t)((k + tc::NC - 1) / tc::NC) * tc::NC;   // centres, padded
     unsigned char *a_img = (unsigned char *)scratch;
-    unsigned char *b_img = a_img + 2 * sizeof(float) * row * a_rows;
-    unsigned char *lists = b_img + 2 * sizeof(float) * row * c_rows;
+    unsigned char *b_img = a_img + row * a_rows;
+    unsigned char *lists = b_img + row * c_rows;
     const int n_ct_total = (k + tc::NC - 1) / tc::NC;
     const long n_ft = (n + tc::BM - 1) / tc::BM;
     const int n_seg = tc_pick_nseg(n_ft, n_ct_total);
@@ -698,20 +735,23 @@ int eb_rmsd_assign_tc(const float *xyz_soa, const double *traces, int64_t n, int
     float *cand_bound = (float *)(cand_list + (size_t)n * n_lists * max_cand);
     float *cand_umin = cand_bound + (size_t)n * n_lists * max_cand;
     int *seg_count = (int *)(cand_umin + (size_t)n * n_lists);
+    // set by the pack kernels when a coordinate does not fit the FP16 split (|x| > 253 nm)
+    int *f16_overflow = (int *)(((uintptr_t)(seg_count + (size_t)n * n_lists) + 15) & ~(uintptr_t)15);
+    EB_CUDA(cudaMemsetAsync(f16_overflow, 0, sizeof(int), s));
 
     {
-        long total = n_ft * tc::BM * 3 * (long)(A_img / 4);
+        long total = n_ft * tc::BM * 3 * (long)(A_img / 8);
         long blocks = (total + 255) / 256;
         if (blocks > 32L * sm_count()) blocks = 32L * sm_count();
-        tc::k_pack_tf32<<<(int)blocks, 256, 0, s>>>(xyz_soa, 3L * n, A_pad, tc::BM, 3, n_ft,
-                                                    frame_idx, a_img);
+        tc::k_pack_f16x2<<<(int)blocks, 256, 0, s>>>(xyz_soa, 3L * n, A_pad, tc::BM, 3, n_ft,
+                                                     frame_idx, a_img, f16_overflow);
         EB_LAUNCH_CHECK();
         const long b_tiles = n_ct_total;
-        total = b_tiles * tc::BN * (long)(A_img / 4);
+        total = b_tiles * tc::BN * (long)(A_img / 8);
         blocks = (total + 255) / 256;
         if (blocks > 32L * sm_count()) blocks = 32L * sm_count();
-        tc::k_pack_tf32<<<(int)blocks, 256, 0, s>>>(centers_soa, 3L * k, A_pad, tc::BN, 1, b_tiles,
-                                                    nullptr, b_img);
+        tc::k_pack_f16x2<<<(int)blocks, 256, 0, s>>>(centers_soa, 3L * k, A_pad, tc::BN, 1,
+                                                     b_tiles, nullptr, b_img, f16_overflow);
         EB_LAUNCH_CHECK();
     }
     const size_t smem = (size_t)tc::STAGES * tc::STAGE_BYTES + sizeof(tc::Smem) + 1024;
@@ -756,9 +796,42 @@ int eb_rmsd_assign_tc(const float *xyz_soa, const double *traces, int64_t n, int
         tc::k_rescore<<<(int)blocks, tc::RS_THREADS, rs_smem, s>>>(
             xyz_soa, traces, n, n_atoms, A_pad, centers_soa, center_traces, seg_count, cand_list,
             cand_bound, cand_umin, (int)n_lists, out_dist, out_assign, cand_count, frame_idx,
-            scatter, max_cand);
+            scatter, max_cand, f16_overflow);
         EB_LAUNCH_CHECK();
     }
+    return EB_OK;
+}
+
+// Exact scoring of explicit per-position centre lists (the re-score kernel on its own): position
+// p covers frame frame_idx[p] (or p) and the list_len-strided list cand_list[p * list_len ..
+// + cand_count[p]); out_dist/out_assign[p] receive the nearest listed centre (exact float64
+// path, lowest index on ties).  Used by the host's audit of the tensor-core screen: a sample of
+// frames is scored against ALL centres, cut into lists of list_len, and compared with what the
+// screen + re-score produced.  bound_lo / bound_up: list_len * n_pos floats of -inf and n_pos
+// floats of +inf (every listed centre is scored); zero_flag: one int holding 0.
+int eb_rmsd_score_lists(const float *xyz_soa, const double *traces, int64_t n_pos, int n_atoms,
+                        const float *centers_soa, const double *center_traces,
+                        const int32_t *cand_count, const int32_t *cand_list, int list_len,
+                        const float *bound_lo, const float *bound_up, const int32_t *zero_flag,
+                        const int64_t *frame_idx, float *out_dist, int32_t *out_assign,
+                        int32_t *frame_flag, void *stream)
+{
+    EB_CHECK_ARG(n_pos >= 0 && n_atoms > 0 && list_len > 0, "rmsd_score_lists: bad shape");
+    if (n_pos == 0) return EB_OK;
+    EB_CHECK_ARG(xyz_soa && traces && centers_soa && center_traces && cand_count && cand_list &&
+                     bound_lo && bound_up && zero_flag && out_dist && out_assign && frame_flag,
+                 "rmsd_score_lists: null pointer");
+    const size_t rs_smem = align16(sizeof(int) * tc::RS_GROUPS * (size_t)list_len);
+    EB_CHECK_ARG(rs_smem <= 227 * 1024, "rmsd_score_lists: lists too long");
+    long blocks = (n_pos + tc::RS_GROUPS - 1) / tc::RS_GROUPS;
+    if (blocks > 10L * sm_count()) blocks = 10L * sm_count();
+    EB_CUDA(cudaFuncSetAttribute(tc::k_rescore, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(rs_smem > 48 * 1024 ? rs_smem : 48 * 1024)));
+    tc::k_rescore<<<(int)blocks, tc::RS_THREADS, rs_smem, (cudaStream_t)stream>>>(
+        xyz_soa, traces, n_pos, n_atoms, rmsd_apad(n_atoms), centers_soa, center_traces,
+        cand_count, cand_list, bound_lo, bound_up, 1, out_dist, out_assign, frame_flag, frame_idx,
+        0, list_len, zero_flag);
+    EB_LAUNCH_CHECK();
     return EB_OK;
 }
 

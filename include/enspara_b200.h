@@ -206,8 +206,9 @@ int eb_rmsd_one_to_all_pruned(const float *xyz_soa, const double *traces, int64_
                               const float *dist, const int32_t *assign, const float *cc,
                               int32_t cid, float *out, void *stream);
 
-/* ---- K3 on the tensor cores: 3xTF32 tcgen05 screen + exact re-score ----------------------
+/* ---- K3 on the tensor cores: split-FP16 tcgen05 screen + exact re-score ------------------
  * Same result as eb_rmsd_assign (dense pass over all n frames, no accumulate): a tcgen05 GEMM
+ * (operands x*2^8 = h1 + h2 in FP16, D = A1.B1 + A1.B2 + A2.B1 accumulated in FP32 in TMEM)
  * with a fused QCP epilogue bounds every (frame, centre) distance; only centres whose lower
  * bound does not exceed the frame's best upper bound survive (error model: |d msd| <=
  * kappa * sqrt(Ga*Gb) / n_atoms) and are re-scored exactly in float64 with the reference's
@@ -217,7 +218,7 @@ int eb_rmsd_one_to_all_pruned(const float *xyz_soa, const double *traces, int64_
  * pass to frames frame_idx[0..n) of xyz_soa (PAM's X[dst_up_assig_this], kmedoids.py:666-667):
  * cand_count is indexed by position, results go to position i or, with `scatter`, to
  * frame_idx[i].  scratch: eb_tc_scratch_bytes(n, n_atoms, k).  Any n_atoms (the packed
- * operand images are zero-padded to a multiple of 16 atoms).  mode 0 is a debugging aid: dbg (n*k*9 floats) receives the
+ * operand images are zero-padded to a multiple of 32 atoms).  mode 0 is a debugging aid: dbg (n*k*9 floats) receives the
  * approximate inner-product matrices and nothing else is written; mode 2 is a timing probe
  * (pack + screen with the QCP epilogue removed; no outputs). */
 size_t eb_tc_scratch_bytes(int64_t n, int n_atoms, int32_t k);
@@ -226,6 +227,19 @@ int eb_rmsd_assign_tc(const float *xyz_soa, const double *traces, int64_t n, int
                       double kappa, const int64_t *frame_idx, int scatter, float *out_dist,
                       int32_t *out_assign, int32_t *cand_count, void *scratch, float *dbg,
                       int mode, void *stream);
+/* Exact scoring of explicit per-position centre lists (the re-score stage on its own; exact
+ * float64 inner products, lowest centre index on ties like cluster/util.py:201): position p
+ * covers frame frame_idx[p] (or p when NULL) and the centres cand_list[p*list_len ..
+ * +cand_count[p]); out_dist / out_assign[p] receive the nearest listed centre.  The host uses it
+ * to AUDIT the tensor-core screen: a sample of frames is scored against every centre and must
+ * reproduce what eb_rmsd_assign_tc wrote.  bound_lo: n_pos*list_len floats of -inf, bound_up:
+ * n_pos floats of +inf, zero_flag: one int32 holding 0 (all device memory). */
+int eb_rmsd_score_lists(const float *xyz_soa, const double *traces, int64_t n_pos, int n_atoms,
+                        const float *centers_soa, const double *center_traces,
+                        const int32_t *cand_count, const int32_t *cand_list, int list_len,
+                        const float *bound_lo, const float *bound_up, const int32_t *zero_flag,
+                        const int64_t *frame_idx, float *out_dist, int32_t *out_assign,
+                        int32_t *frame_flag, void *stream);
 
 /* ---- K3 for feature vectors (same contract as eb_rmsd_assign) */
 int eb_feat_assign(const void *X, int64_t n, int64_t n_features, int dtype, int metric,

@@ -13,7 +13,7 @@ scratch = torch.empty(int(L.eb_tc_scratch_bytes(n, A, k)), dtype=torch.uint8, de
 od = torch.empty(n, dtype=torch.float32, device="cuda"); oa = torch.empty(n, dtype=torch.int32, device="cuda")
 cand = torch.empty(n, dtype=torch.int32, device="cuda")
 dbg = torch.zeros(16, dtype=torch.float32, device="cuda")
-kappa = _ops.TC_KAPPA_PER_ATOM * data.a_pad
+kappa = _ops.tc_kappa(data.a_pad)
 for mode in (1, 2, 1, 2):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     torch.cuda.synchronize(); ev[0].record()

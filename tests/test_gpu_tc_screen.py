@@ -1,6 +1,9 @@
-"""GPU parity: the tcgen05 3xTF32 screen + exact re-score returns EXACTLY what the exact float64
-many-centres kernel returns (assignments and float32 distances, bit for bit), and the oracle's
-result within the RMSD tolerance."""
+"""GPU parity: the tcgen05 split-FP16 screen + exact re-score returns EXACTLY what the exact
+float64 many-centres kernel returns (assignments and float32 distances, bit for bit), and the
+ORACLE's result (restated mdtraj RMSD driven by the reference's assign loop,
+cluster/util.py:159-205) within the RMSD tolerance -- including at the BASELINE config-5 shape
+(500 atoms, >= 1000 centres).  Also: the error bound the screen's discard rule rests on
+(cluster/_ops.py TC_KAPPA) holds entry by entry, and the built-in audit runs."""
 import numpy as np
 import pytest
 from numpy.testing import assert_allclose, assert_array_equal
@@ -142,4 +145,144 @@ def test_tc_any_atom_count(cuda, n, A, k):
     assert _ops.tc_applicable(util.RMSD, data, k)
     d0, a0 = _ops.assign_device(util.RMSD, data, cen)
     d1, a1 = _ops.assign_device_tc(util.RMSD, data, cen)
+    assert cuda.equal(a0, a1) and cuda.equal(d0, d1)
+
+
+def _oracle_assign_sample(X, centre_idx, sample, rtol=1e-5, atol=1e-6):
+    """GPU assign of ALL frames of X to the centres X[centre_idx] (tensor-core path) vs the
+    oracle on the sampled frames.  Index mismatches are allowed only as documented near-ties
+    (< 1e-6 nm between the two candidates, north_star)."""
+    from enspara_b200.cluster import util
+    from oracle import cluster as oc
+    from oracle import distances as od
+    T = od.Trajectory(X)
+    centers = [T[int(i)] for i in centre_idx]
+    got_a, got_d = util.assign_to_nearest_center(T, centers, "rmsd")
+    S = od.Trajectory(X[sample])
+    want_a, want_d = oc.assign_to_nearest_center(S, centers, od.rmsd)
+    assert_allclose(got_d[sample], want_d, rtol=rtol, atol=atol)
+    diff = np.nonzero(got_a[sample] != want_a)[0]
+    for i in diff:      # a different index must be a tie below 1e-6 nm
+        other = od.rmsd(od.Trajectory(X[sample[i]][None]), centers[int(got_a[sample][i])])[0]
+        assert abs(float(other) - float(want_d[i])) < 1e-6
+    return len(diff)
+
+
+def test_tc_assign_matches_oracle_at_config5_shape(cuda):
+    """BASELINE configs[4] shape: 500 atoms, 1200 centres (25 centre tiles, several segments);
+    60 000 frames through the screen, 300 of them checked against the oracle."""
+    from enspara_b200 import synth
+    from enspara_b200.cluster import _ops
+    n, A, k = 60_000, 500, 1200
+    X = synth.device_trajectory_aos(n, A, seed=0).cpu().numpy()
+    rs = np.random.RandomState(1)
+    centre_idx = np.sort(rs.choice(n, k, replace=False))
+    sample = np.sort(rs.choice(n, 300, replace=False))
+    before = dict(_ops.audit_stats)
+    _oracle_assign_sample(X, centre_idx, sample)
+    # the dense pass was audited (>= 2^24 pairs): 64 frames exact-scored against all centres
+    assert _ops.audit_stats["passes_audited"] > before["passes_audited"]
+
+
+@pytest.mark.parametrize("n,A,k", [(20_000, 264, 1000), (30_000, 22, 2000)])
+def test_tc_assign_matches_oracle_other_atom_counts(cuda, n, A, k):
+    """Config-1-like (264 atoms) and frame0-like (22 atoms) molecules with >= 1000 centres."""
+    from enspara_b200 import synth
+    X = synth.device_trajectory_aos(n, A, seed=3).cpu().numpy()
+    rs = np.random.RandomState(2)
+    centre_idx = np.sort(rs.choice(n, k, replace=False))
+    sample = np.sort(rs.choice(n, 400, replace=False))
+    _oracle_assign_sample(X, centre_idx, sample)
+
+
+def test_tc_error_bound(cuda):
+    """The inequality the discard rule is derived from, checked entry by entry on the
+    accumulators the tensor core really produced (mode 0 dumps them):
+        |M_tc[f,c,i,j] - M_exact[f,c,i,j]| <= (3.19 A + 3) 2^-23 sqrt(Gx_i(f) Gy_j(c)),
+    and its consequence for N * msd with kappa = _ops.tc_kappa(A_pad).  Reports how far the
+    observed worst case is from the bound (expected: well below 1)."""
+    torch = cuda
+    from enspara_b200 import _lib, synth
+    from enspara_b200.cluster import _ops
+    from enspara_b200.device import DeviceTrajectory, ptr, stream_ptr
+    L = _lib.load()
+    worst_entry = worst_msd = 0.0
+    for n, k, A, seed in ((1024, 96, 500, 3), (512, 144, 1000, 4), (2048, 48, 264, 5),
+                          (700, 50, 22, 6)):
+        data = DeviceTrajectory.from_host(synth.trajectory(n, A, seed=seed))
+        cen = data.gather(np.linspace(0, n - 1, k).astype(np.int64))
+        scratch = torch.zeros(int(L.eb_tc_scratch_bytes(n, A, k)), dtype=torch.uint8,
+                              device="cuda")
+        dbg = torch.zeros((n, k, 9), dtype=torch.float32, device="cuda")
+        _lib.call("eb_rmsd_assign_tc", ptr(data.xyz), ptr(data.traces), n, A, ptr(cen.xyz),
+                  ptr(cen.traces), k, 0.0, None, 0, None, None, None, ptr(scratch), ptr(dbg), 0,
+                  stream_ptr())
+        xs = data.xyz.double()                               # (n, 3, A_pad) centred
+        cs = cen.xyz.double()
+        M = torch.einsum("fia,cja->fcij", xs, cs)
+        dM = (dbg.double().view(n, k, 3, 3) - M).abs()
+        gx = (xs * xs).sum(dim=2)                            # (n, 3) per-coordinate traces
+        gy = (cs * cs).sum(dim=2)
+        bound = (3.19 * data.a_pad + 3.0) * 2.0 ** -23 * torch.sqrt(
+            gx[:, None, :, None] * gy[None, :, None, :])
+        ratio = float((dM / bound.clamp(min=1e-300)).max())
+        worst_entry = max(worst_entry, ratio)
+        assert ratio < 1.0, "entry bound violated (n=%d k=%d A=%d): %.3g" % (n, k, A, ratio)
+        # consequence: |d lambda| <= sqrt(3) ||dM||_F  ->  |d(N msd)| <= kappa sqrt(Ga Gb)
+        fro = torch.sqrt((dM * dM).sum(dim=(2, 3)))
+        lhs = 2.0 * 3.0 ** 0.5 * fro
+        rhs = _ops.tc_kappa(data.a_pad) * torch.sqrt(data.traces[:, None] * cen.traces[None, :])
+        worst_msd = max(worst_msd, float((lhs / rhs).max()))
+        assert bool((lhs <= rhs).all())
+    print("tc error bound: worst entry ratio %.4f, worst N*msd ratio %.4f of the bound"
+          % (worst_entry, worst_msd))
+    assert worst_entry < 0.5        # the bound is meant to have margin, not to be tight
+
+
+def test_tc_audit_every_call_and_detects_corruption(cuda, monkeypatch):
+    """ENSPARA_B200_TC_AUDIT=2 audits every pass, subsets included; an assignment the exact
+    path disagrees with raises."""
+    torch = cuda
+    from enspara_b200 import synth
+    from enspara_b200.cluster import _ops, util
+    from enspara_b200.device import DeviceTrajectory
+    monkeypatch.setenv("ENSPARA_B200_TC_AUDIT", "2")
+    data = DeviceTrajectory.from_host(synth.trajectory(4000, 96, seed=8))
+    cen = data.gather(np.linspace(0, 3999, 300).astype(np.int64))
+    before = _ops.audit_stats["passes_audited"]
+    d1, a1 = _ops.assign_device_tc(util.RMSD, data, cen)
+    idx = torch.arange(5, 3000, 7, device="cuda")
+    d = torch.full((4000,), -1.0, device="cuda")
+    a = torch.full((4000,), -1, dtype=torch.int32, device="cuda")
+    _ops.assign_device_tc(util.RMSD, data, cen, frame_idx=idx, out_dist=d, out_assign=a,
+                          scatter=True)
+    assert _ops.audit_stats["passes_audited"] == before + 2
+    assert torch.equal(a[idx], a1[idx]) and torch.equal(d[idx], d1[idx])
+    # corrupt what the audit compares against: it must notice
+    ws = {}
+    real = _ops._audit_tc
+
+    def corrupting(data_, centers_, k_, m_, fi_, sc_, od_, oa_, ws_):
+        oa_.add_(1)
+        return real(data_, centers_, k_, m_, fi_, sc_, od_, oa_, ws_)
+    monkeypatch.setattr(_ops, "_audit_tc", corrupting)
+    with pytest.raises(RuntimeError, match="audit FAILED"):
+        _ops.assign_device_tc(util.RMSD, data, cen, workspace=ws)
+
+
+def test_tc_fp16_range_overflow_falls_back_to_exact(cuda):
+    """Coordinates beyond the FP16 split's range (|x| * 2^8 > 65000, i.e. > 253 nm from the
+    centroid) cannot go through the screen: the pack kernel flags it and every frame takes the
+    exact kernel -- same result."""
+    from enspara_b200 import synth
+    from enspara_b200.cluster import _ops, util
+    from enspara_b200.device import DeviceTrajectory
+    X = synth.trajectory(2000, 40, seed=9) * np.float32(200.0)       # extents of several hundred nm
+    assert np.abs(X - X.mean(axis=1, keepdims=True)).max() > 260.0
+    data = DeviceTrajectory.from_host(X)
+    cen = data.gather(np.linspace(0, 1999, 70).astype(np.int64))
+    d0, a0 = _ops.assign_device(util.RMSD, data, cen)
+    stats = {}
+    d1, a1 = _ops.assign_device_tc(util.RMSD, data, cen, stats=stats)
+    assert stats["overflow_frames"] == 2000
     assert cuda.equal(a0, a1) and cuda.equal(d0, d1)
