@@ -107,3 +107,41 @@ def modules():
     return (m["enspara.cluster.kcenters"], m["enspara.cluster.kmedoids"],
             m["enspara.cluster.hybrid"], m["enspara.cluster.util"],
             m["enspara.geometry.libdist"], m["enspara.mpi"])
+
+
+def load_compiled_libdist():
+    """The reference's OWN compiled Cython ``libdist`` (oracle/_ref/, built by build_libdist()
+    from /root/reference/enspara/geometry/libdist.pyx) WITHOUT the reference's Python package:
+    the only thing the extension imports from it is ``enspara.exception`` (libdist.pyx:4), which
+    is stubbed here.  This is what travels to the GPU box, where /root/reference does not
+    exist: bench CPU baselines time the reference's real euclidean / manhattan code there."""
+    import glob
+    import importlib.util
+    name = "enspara.geometry.libdist"
+    if name in sys.modules and hasattr(sys.modules[name], "euclidean"):
+        return sys.modules[name]
+    hits = glob.glob(os.path.join(_GEOM_DIR, "libdist*.so"))
+    if not hits:
+        if not available():
+            raise RuntimeError("oracle/_ref/enspara_geometry/libdist*.so is missing and the "
+                               "reference tree is not present to build it")
+        hits = [build_libdist()]
+    if "enspara" not in sys.modules:
+        pkg = types.ModuleType("enspara")
+        pkg.__path__ = []
+        exc = types.ModuleType("enspara.exception")
+
+        class ImproperlyConfigured(Exception):
+            pass
+
+        class DataInvalid(Exception):
+            pass
+        exc.ImproperlyConfigured, exc.DataInvalid = ImproperlyConfigured, DataInvalid
+        pkg.exception = exc
+        sys.modules["enspara"] = pkg
+        sys.modules["enspara.exception"] = exc
+    spec = importlib.util.spec_from_file_location(name, hits[0])
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    sys.modules[name] = mod
+    return mod

@@ -20,12 +20,42 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 PEAK = 6550.4
+TENSOR_PEAK = 1575.1       # TFLOP/s, dense bf16/fp16 burst (MEASURED_PEAKS.json)
 try:
     with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                            "MEASURED_PEAKS.json")) as fh:
-        PEAK = float(json.load(fh)["hbm_gbs"])
+        _pk = json.load(fh)
+        PEAK = float(_pk["hbm_gbs"])
+        TENSOR_PEAK = float(_pk.get("bf16_tflops", TENSOR_PEAK))
 except Exception:
     pass
+
+
+def tensor_peaks():
+    """cuBLAS dense GEMM peaks on THIS box (8192^3, best of 10, CUDA events): fp16 with FP32
+    accumulation (what the K3t screen executes) and TF32 (what SURVEY 8d asked to be measured
+    for the 3xTF32 formulation of round 1).  cuBLAS is used for the PEAK only."""
+    out = {}
+    n = 8192
+    for name, dt, tf32 in (("fp16", torch.float16, False), ("tf32", torch.float32, True)):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        a = torch.randn(n, n, device="cuda", dtype=dt)
+        b = torch.randn(n, n, device="cuda", dtype=dt)
+        for _ in range(3):
+            a @ b
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        out[name + "_tflops"] = 2 * n ** 3 / (best * 1e-3) / 1e12
+        del a, b
+    torch.backends.cuda.matmul.allow_tf32 = False
+    out["how"] = "torch.matmul 8192^3 (cuBLAS), best of 10, CUDA events"
+    return out
 
 
 def sync():
@@ -113,7 +143,10 @@ def c5(n=1_250_000, A=500, k=10_000):
     out = {"config": "C5 assign_to_nearest_center, %d centres x %d frames x %d atoms (one "
                      "GPU's shard of 10M; centres replicated, no exchange)" % (k, n, A),
            "seconds": dt, "evals_per_s": evs, "algorithmic_TFLOPs": evs * 18 * A / 1e12,
-           "executed_TF32_TFLOPs": evs * 54 * 512 / 1e12, "centres_assigned_to_themselves": self_ok,
+           "executed_FP16_TFLOPs": evs * 54 * 512 / 1e12,
+           "frac_of_measured_bf16_peak_executed": evs * 54 * 512 / 1e12 / TENSOR_PEAK,
+           "frac_of_measured_bf16_peak_algorithmic": evs * 18 * A / 1e12 / TENSOR_PEAK,
+           "centres_assigned_to_themselves": self_ok,
            "survivors_per_frame": stats.get("survivors_mean"),
            "overflow_frames": stats.get("overflow_frames")}
     # the same pass with centres CHOSEN BY K-CENTERS (spread out: what assign/reassign sees in
@@ -205,9 +238,12 @@ def main():
     p = argparse.ArgumentParser()
     p.add_argument("--out", default="gpurun_out/configs.json")
     p.add_argument("--only", default="c1,c2,c3,c5,reassign")
+    p.add_argument("--no-cpu", action="store_true",
+                   help="skip the CPU baselines beside c1/c2/c3/c5 (scripts/cpu_baselines.py)")
     args = p.parse_args()
     torch.cuda.set_device(0)
-    fns = {"c1": c1, "c2": c2, "c3": c3, "c5": c5, "reassign": reassign, "tri": tri}
+    fns = {"c1": c1, "c2": c2, "c3": c3, "c5": c5, "reassign": reassign, "tri": tri,
+           "peaks": tensor_peaks}
     results = {}
     for name in args.only.split(","):
         try:
@@ -215,6 +251,10 @@ def main():
         except Exception as exc:  # keep going: one failing config must not hide the others
             import traceback
             results[name] = {"error": repr(exc), "trace": traceback.format_exc()[-1500:]}
+        if not args.no_cpu and name in ("c1", "c2", "c3", "c5") and "error" not in results[name]:
+            # the reference's CPU path for the same config, same run, same host
+            from scripts import cpu_baselines
+            results[name]["cpu_baseline"] = cpu_baselines.run((name,)).get(name)
         print(name, json.dumps(results[name]), flush=True)
         torch.cuda.empty_cache()
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
