@@ -157,6 +157,38 @@ def test_kcenters_synthetic_c1_matches_oracle(cuda):
     assert mism.mean() < 1e-3
 
 
+def test_kcenters_config1_full_size_matches_oracle(cuda):
+    """BASELINE configs[0] at FULL size: KCenters rmsd n_clusters=100 on 20 000 frames x 264
+    atoms, through the estimator, against the oracle (2M float64 RMSD evaluations, seconds):
+    centre sequence, assignments, distances."""
+    from enspara_b200.cluster import KCenters
+    from oracle import cluster as oc
+    from oracle import distances as od
+    od.use_all_cores()
+    X = od.synth_trajectory(20_000, 264, seed=0)     # bit-identical to enspara_b200.synth
+    T = od.Trajectory(X)
+    trace = []
+    ref = oc.kcenters(T, od.rmsd, n_clusters=100, trace=trace)
+    est = KCenters("rmsd", n_clusters=100).fit(T)
+    got = est.result_
+    got_c = [int(c) for c in got.center_indices]
+
+    def d_oracle(i, c):
+        a, d = oc.assign_to_nearest_center(T[[c]], [T[j] for j in ref.center_indices[:i]],
+                                           od.rmsd) if i else (None, [np.inf])
+        return d[0]
+    _assert_lockstep(trace, got_c, d_oracle)
+    assert got_c == [int(c) for c in ref.center_indices]
+    np.testing.assert_allclose(got.distances, ref.distances, rtol=RTOL, atol=ATOL)
+    mism = np.where(got.assignments != ref.assignments)[0]
+    for f in mism:      # only allowed where the two nearest centres are a near-tie
+        d_all = np.array([od.rmsd(T[[f]], T[c])[0] for c in ref.center_indices])
+        top2 = np.sort(d_all)[:2]
+        assert top2[1] - top2[0] < ATOL
+    assert len(mism) < 20
+    assert got.assignments.dtype == np.int64 and got.distances.dtype == np.float64
+
+
 def test_kcenters_cutoff_and_limit_interplay(cuda):
     from enspara_b200 import synth
     from enspara_b200.cluster import kcenters
