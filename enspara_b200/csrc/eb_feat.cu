@@ -15,6 +15,8 @@
 // tile of 32 rows x 256 bytes into shared memory with 16-byte vector loads (two rows per
 // request), padded so the per-lane 16-byte reads are bank-conflict free.  HBM bound: each row
 // byte is read once; dist (float64) is a coalesced read-modify-write.
+#include <stdlib.h>
+
 #include "eb_tma.cuh"
 
 namespace eb {
@@ -360,6 +362,264 @@ k_kcenters_step_feat(const T *__restrict__ X, long n, long F, long frame_offset,
 }
 
 // ------------------------------------------------------------------------------------------
+// Persistent multi-iteration step (single shard, TMA path): up to n_steps iterations of
+// kcenters.py:217-226 in ONE cooperative launch.  A launch per iteration costs ~18 us of fixed
+// overhead at 1M x 64 (launch gap, prologue round trips, DRAM ramp, the single-CTA arg-max
+// tail) on top of a 41 us HBM-bound body; here the grid stays resident, the shard arg-max is
+// a grid barrier after which EVERY block reduces the per-block partials itself (no serial
+// last-block tail), the winner's row is read straight from X, and the TMA ring keeps running
+// across the barrier (the first tiles of iteration i+1 are in flight while iteration i's
+// arg-max is being agreed on -- X does not change).  Same arithmetic, same tie rules, same
+// state protocol as k_kcenters_step_feat<T, METRIC, kFStep>: on exit cand holds the next
+// candidate record and *state the counters, so single launches and multi launches mix freely.
+// gbar: monotonically increasing arrival counter (a multiple of gridDim.x between launches).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <typename T, int METRIC>
+__global__ void __launch_bounds__(kFeatThreads)
+k_kcenters_multi_feat(const T *__restrict__ X, long n, long F, long frame_offset,
+                      unsigned char *cand, size_t rec_bytes, double *dist, int *assign,
+                      int n_clusters_limit, double cutoff, eb_kc_state *state,
+                      int64_t *center_list, Partial *partials, unsigned long long *gbar,
+                      int n_steps, const __grid_constant__ CUtensorMap tmap)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *tiles = smem_raw;
+    FeatSmem *ss = reinterpret_cast<FeatSmem *>(tiles + (size_t)kFeatWarps * 2 * kTmaTileBytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(ss) +
+                                                  align16(sizeof(FeatSmem)));
+    T *y_sh = reinterpret_cast<T *>(bars + 2 * kFeatWarps);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned G = gridDim.x;
+    if (lane == 0) {
+        mbar_init(bars + 2 * warp, 1);
+        mbar_init(bars + 2 * warp + 1, 1);
+        fence_mbar_init();
+        tma_prefetch_desc(&tmap);
+    }
+    __syncwarp();
+
+    // nobody writes *state / *gbar's base before the first barrier, so these reads agree
+    const int k0 = *reinterpret_cast<const volatile int32_t *>(&state->n_centers);
+    const int done0 = *reinterpret_cast<const volatile int32_t *>(&state->done);
+    const unsigned long long gbase = (ld_acquire_gpu_u64(gbar) / G) * G;
+
+    constexpr int EPT = kTileBytes / (int)sizeof(T);
+    constexpr int EPB = 128 / (int)sizeof(T);
+    const int nt = (int)((F + EPT - 1) / EPT);
+    const long n_chunks = (n + 31) >> 5;
+    const long warps_total = (long)G * kFeatWarps;
+    const long first_chunk = (long)blockIdx.x * kFeatWarps + warp;
+    const bool has_work = first_chunk < n_chunks;
+    unsigned char *tile = tiles + (size_t)warp * 2 * kTmaTileBytes;
+    uint64_t *bar = bars + 2 * warp;
+
+    // producer cursor: (iteration, chunk, tile); runs at most two tiles ahead of the consumer
+    int p_iter = 0, p_jt = 0, p_buf = 0, inflight = 0;
+    long p_chunk = first_chunk;
+    auto try_issue = [&]() {
+        if (!has_work || p_iter >= n_steps || inflight >= 2) return;
+        if (lane == 0) {
+            const long j0 = (long)p_jt * EPT;
+            const int fe = (int)min((long)EPT, F - j0);
+            const int n_box = (fe + EPB - 1) / EPB;
+            unsigned char *dst = tile + p_buf * kTmaTileBytes;
+            mbar_expect_tx(bar + p_buf, (uint32_t)n_box * kBoxBytes);
+            for (int b = 0; b < n_box; ++b)
+                tma_load_2d(dst + b * kBoxBytes, &tmap, (int)(j0 + (long)b * EPB),
+                            (int)(p_chunk << 5), bar + p_buf);
+        }
+        p_buf ^= 1;
+        ++inflight;
+        if (++p_jt == nt) {
+            p_jt = 0;
+            p_chunk += warps_total;
+            if (p_chunk >= n_chunks) {
+                p_chunk = first_chunk;
+                ++p_iter;
+            }
+        }
+    };
+    uint32_t phase0 = 0, phase1 = 0;
+    int c_buf = 0;
+    auto wait_tile = [&]() {
+        mbar_wait(bar + c_buf, c_buf ? phase1 : phase0);
+        if (c_buf) phase1 ^= 1; else phase0 ^= 1;
+    };
+    try_issue();     // the first tile does not depend on the centre: start it right away
+
+    int it = 0;
+    bool stopped = false;
+    double win_d = 0.0;        // distance / global index of the winner examined last
+    int64_t win_i = -1;
+    for (; it < n_steps; ++it) {
+        // ---- the centre of this iteration: candidate record (first) or the partials ---------
+        const T *src;
+        bool have;
+        if (it == 0) {
+            const RecHeader *h = reinterpret_cast<const RecHeader *>(cand);
+            win_d = __ldcg(&h->dist);
+            win_i = __ldcg(reinterpret_cast<const long long *>(&h->index));
+            have = win_i >= 0;
+            src = reinterpret_cast<const T *>(cand + sizeof(RecHeader));
+        } else {
+            const Partial *pp = partials + (size_t)((it - 1) & 1) * G;
+            double d = -2.0;
+            int64_t i = INT64_MAX;
+            for (unsigned b = threadIdx.x; b < G; b += blockDim.x) {
+                const double od = __ldcg(&pp[b].dist);
+                const int64_t oi = __ldcg(reinterpret_cast<const long long *>(&pp[b].index));
+                if (better(od, oi, d, i)) {
+                    d = od;
+                    i = oi;
+                }
+            }
+            block_argmax(d, i, ss->red);
+            if (threadIdx.x == 0) {
+                ss->red[0].dist = d;
+                ss->red[0].index = i;
+            }
+            __syncthreads();
+            d = ss->red[0].dist;
+            i = ss->red[0].index;
+            __syncthreads();
+            have = i != INT64_MAX;
+            win_d = have ? d : -1.0;
+            win_i = have ? frame_offset + i : -1;
+            src = X + (have ? i : 0) * F;
+        }
+        const int k = k0 + it;
+        if (!(have && !done0 && k < n_clusters_limit && win_d > cutoff)) {   // kcenters.py:217
+            stopped = true;
+            break;
+        }
+        for (long j = threadIdx.x; j < F; j += blockDim.x) y_sh[j] = src[j];
+        if (blockIdx.x == 0 && threadIdx.x == 0) center_list[k] = win_i;
+        __syncthreads();
+
+        // ---- body: every row once, strict '<' update, arg-max --------------------------------
+        double best_d = -2.0;
+        int64_t best_i = INT64_MAX;
+        double acc = 0.0;
+        for (long c_chunk = first_chunk; c_chunk < n_chunks; c_chunk += warps_total) {
+            for (int c_jt = 0; c_jt < nt; ++c_jt) {
+                try_issue();
+                wait_tile();
+                const long j0 = (long)c_jt * EPT;
+                const int fe = (int)min((long)EPT, F - j0);
+                acc = tile_terms_swz<T, METRIC>(acc, tile + c_buf * kTmaTileBytes, lane, y_sh, j0,
+                                                fe);
+                if (c_jt == nt - 1) {
+                    const long row = (c_chunk << 5) + lane;
+                    if (row < n) {
+                        const double d = finish<METRIC>(acc);
+                        const double old = dist[row];
+                        if (d < old) {  // strict '<', kcenters.py:304
+                            dist[row] = d;
+                            assign[row] = k;
+                        }
+                        const double cur = (d < old) ? d : old;
+                        if (cur > best_d) {
+                            best_d = cur;
+                            best_i = row;
+                        }
+                    }
+                    acc = 0.0;
+                }
+                c_buf ^= 1;
+                --inflight;
+                __syncwarp();  // everyone is done with this buffer before it is refilled
+                try_issue();
+            }
+        }
+        // ---- shard arg-max: per-block partial, grid barrier ------------------------------------
+        block_argmax(best_d, best_i, ss->red);
+        if (threadIdx.x == 0) {
+            Partial *pp = partials + (size_t)(it & 1) * G;
+            pp[blockIdx.x].dist = best_d;
+            pp[blockIdx.x].index = best_i;
+            __threadfence();
+            atomicAdd(gbar, 1ull);
+            const unsigned long long target = gbase + (unsigned long long)(it + 1) * G;
+            while (ld_acquire_gpu_u64(gbar) < target) {
+            }
+        }
+        __syncthreads();
+    }
+
+    // tiles requested for an iteration that will not run must land before the CTA exits
+    while (inflight > 0) {
+        wait_tile();
+        c_buf ^= 1;
+        --inflight;
+    }
+    if (blockIdx.x != 0) return;
+
+    // ---- block 0: leave *state and the candidate record as a chain of single steps would ----
+    if (it > 0) {
+        const Partial *pp = partials + (size_t)((it - 1) & 1) * G;
+        double d = -2.0;
+        int64_t i = INT64_MAX;
+        for (unsigned b = threadIdx.x; b < G; b += blockDim.x) {
+            const double od = __ldcg(&pp[b].dist);
+            const int64_t oi = __ldcg(reinterpret_cast<const long long *>(&pp[b].index));
+            if (better(od, oi, d, i)) {
+                d = od;
+                i = oi;
+            }
+        }
+        block_argmax(d, i, ss->red);
+        if (threadIdx.x == 0) {
+            ss->red[0].dist = d;
+            ss->red[0].index = i;
+        }
+        __syncthreads();
+        d = ss->red[0].dist;
+        i = ss->red[0].index;
+        const bool empty = (i == INT64_MAX);
+        RecHeader *out = reinterpret_cast<RecHeader *>(cand);
+        if (!empty) {
+            const T *srow = X + i * F;
+            T *dst = reinterpret_cast<T *>(cand + sizeof(RecHeader));
+            for (long j = threadIdx.x; j < F; j += blockDim.x) dst[j] = srow[j];
+        }
+        if (threadIdx.x == 0) {
+            out->dist = empty ? -1.0 : d;
+            out->index = empty ? -1 : frame_offset + i;
+            out->trace = 0.0;
+            out->reserved = 0;
+            state->n_centers = k0 + it;
+            state->last_center = center_list[k0 + it - 1];
+            state->local_maxdist = empty ? -1.0 : d;
+        }
+    }
+    if (threadIdx.x == 0) {
+        if (stopped) {
+            if (!done0) {
+                state->done = 1;
+                state->maxdist = win_d;
+                state->n_noop += n_steps - it - 1;
+            } else {
+                state->n_noop += n_steps;
+            }
+        } else {
+            // the distance of the LAST chosen centre's candidate (what the last prologue saw)
+            state->maxdist = win_d;
+        }
+        state->blocks_done = 0;
+        __threadfence();
+    }
+    (void)rec_bytes;
+}
+
+// ------------------------------------------------------------------------------------------
 // many centres: every row against k centres in order, strict '<'.  A warp owns 32 rows and
 // re-stages them per centre from L1/L2 (k is small whenever this path matters for features).
 // ------------------------------------------------------------------------------------------
@@ -528,6 +788,85 @@ static int launch_feat(const void *X, long n, long F, long frame_offset, const v
     return EB_OK;
 }
 
+// Persistent multi-iteration launch (single shard).  Returns EB_OK with *used = 0 when the
+// shape is not eligible (no 128-byte TMA boxes, too few rows, cooperative launch unsupported):
+// the caller then queues single steps.
+template <typename T, int METRIC>
+static int launch_feat_multi(const void *X, long n, long F, long frame_offset, void *cand,
+                             double *dist, int *assign, int limit, double cutoff,
+                             eb_kc_state *state, int64_t *center_list, void *partials,
+                             int n_steps, cudaStream_t stream, int *used)
+{
+    *used = 0;
+    const size_t smem = feat_smem(F, sizeof(T), 1);
+    if (smem > 227 * 1024) return EB_OK;
+    const bool vec_ok = (((size_t)F * sizeof(T)) % 16 == 0) && (((uintptr_t)X) % 16 == 0) &&
+                        n > 0 && n < (1L << 31) && F < (1L << 31) &&
+                        (size_t)min((long)(128 / sizeof(T)), F) * sizeof(T) == 128;
+    if (!vec_ok) return EB_OK;
+    static int coop = -1;
+    if (coop < 0) {
+        int dev = 0, v = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev);
+        coop = v;
+    }
+    if (!coop) return EB_OK;
+    auto kern = k_kcenters_multi_feat<T, METRIC>;
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     227 * 1024));
+        configured = 227 * 1024;
+    }
+    int per_sm = 0;
+    EB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFeatThreads, smem));
+    if (per_sm < 1) return EB_OK;
+    int grid = feat_grid(n, smem);
+    const long cap = (long)per_sm * sm_count();
+    if (grid > cap) grid = (int)cap;
+    if (2 * grid > kMaxGrid) return EB_OK;       // two partial buffers of `grid` entries
+    CUtensorMap tmap;
+    const int rc = make_tmap_2d(&tmap, X, tmap_dtype<T>(), sizeof(T), (uint64_t)n, (uint64_t)F,
+                                (uint64_t)F * sizeof(T), 32, (uint32_t)(128 / sizeof(T)),
+                                CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != EB_OK) return rc;
+    const T *Xp = (const T *)X;
+    unsigned char *candp = (unsigned char *)cand;
+    size_t rec_bytes = sizeof(RecHeader) + align16((size_t)F * sizeof(T));
+    Partial *pp = (Partial *)partials;
+    unsigned long long *gbar = reinterpret_cast<unsigned long long *>(&state->reserved);
+    void *args[] = {&Xp, &n, &F, &frame_offset, &candp, &rec_bytes, &dist, &assign, &limit,
+                    &cutoff, &state, &center_list, &pp, &gbar, &n_steps, &tmap};
+    EB_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(kFeatThreads), args,
+                                        smem, stream));
+    *used = 1;
+    return EB_OK;
+}
+
+template <typename T, typename... Args> static int dispatch_multi_metric(int metric, Args... args)
+{
+    switch (metric) {
+        case EB_METRIC_EUCLIDEAN: return launch_feat_multi<T, EB_METRIC_EUCLIDEAN>(args...);
+        case EB_METRIC_MANHATTAN: return launch_feat_multi<T, EB_METRIC_MANHATTAN>(args...);
+        case EB_METRIC_SQEUCLIDEAN: return launch_feat_multi<T, EB_METRIC_SQEUCLIDEAN>(args...);
+    }
+    return fail(EB_ERR_INVALID, "%s", "unknown metric");
+}
+
+template <typename... Args> static int dispatch_multi(int dtype, int metric, Args... args)
+{
+    switch (dtype) {
+        case EB_DT_F32: return dispatch_multi_metric<float>(metric, args...);
+        case EB_DT_F64: return dispatch_multi_metric<double>(metric, args...);
+        case EB_DT_I8: return dispatch_multi_metric<int8_t>(metric, args...);
+        case EB_DT_I16: return dispatch_multi_metric<int16_t>(metric, args...);
+        case EB_DT_I32: return dispatch_multi_metric<int32_t>(metric, args...);
+        case EB_DT_I64: return dispatch_multi_metric<int64_t>(metric, args...);
+    }
+    return fail(EB_ERR_INVALID, "%s", "unknown dtype");
+}
+
 template <typename T, int MODE, typename... Args>
 static int dispatch_metric(int metric, Args... args)
 {
@@ -610,6 +949,21 @@ int eb_kcenters_step_feat(const void *X, int64_t n, int64_t n_features, int dtyp
     EB_CHECK_ARG(elem_size(dtype) != 0, "kcenters_step_feat: unknown dtype");
     EB_CHECK_ARG(n_cand >= 1 && cand_in && cand_out && state && partials && center_list,
                  "kcenters_step_feat: null pointer / n_cand < 1");
+    // EB_K2_MULTI=0 forces one launch per iteration (developer A/B switch)
+    static const int multi_on = [] {
+        const char *e = getenv("EB_K2_MULTI");
+        return e ? atoi(e) : 1;
+    }();
+    if (n_steps > 1 && multi_on) {
+        // single shard: all iterations in one persistent cooperative launch when eligible
+        int used = 0;
+        const int rc = dispatch_multi(dtype, metric, X, (long)n, (long)n_features,
+                                      (long)frame_offset, cand_out, dist, assign,
+                                      (int)n_clusters_limit, dist_cutoff, state, center_list,
+                                      partials, n_steps, (cudaStream_t)stream, &used);
+        if (rc != EB_OK) return rc;
+        if (used) return EB_OK;
+    }
     for (int it = 0; it < n_steps; ++it) {
         const int rc = dispatch<kFStep>(dtype, metric, X, (long)n, (long)n_features,
                                         (long)frame_offset, cand_in, n_cand, dist, assign,

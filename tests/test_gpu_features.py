@@ -152,3 +152,102 @@ def test_unknown_callable_rejected(cuda):
         kcenters.kcenters(np.zeros((4, 2)), "euclidean")
     with pytest.raises(NotImplementedError):
         kcenters.kcenters(np.zeros((4, 2)), "euclidean", n_clusters=2, random_first_center=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# persistent multi-iteration step (csrc/eb_feat.cu k_kcenters_multi_feat): rows of whole
+# 128-byte boxes on a single shard run ALL iterations of a batch in one cooperative launch
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,F", [(np.float32, 64), (np.float32, 32), (np.float32, 96),
+                                     (np.float64, 16), (np.float64, 48), (np.int8, 128),
+                                     (np.int16, 64), (np.int32, 32), (np.int64, 16)])
+def test_multi_iteration_kernel_bit_exact(cuda, dtype, F):
+    """n_clusters-bounded, cutoff-terminated (stop inside a 32-launch batch and exactly at a
+    batch boundary) and both bounds at once -- centres, assignments, float64 distances equal to
+    the oracle's (= the reference's own compiled libdist, tests/test_oracle_ref.py)."""
+    from enspara_b200.cluster import kcenters
+    from oracle import cluster as oc
+    from oracle import distances as od
+    rng = np.random.default_rng(int(F) + np.dtype(dtype).itemsize)
+    n = 20_011
+    if np.issubdtype(dtype, np.integer):
+        X = rng.integers(-100, 100, (n, F)).astype(dtype)
+    else:
+        X = rng.random((n, F)).astype(dtype)
+    trace = []
+    ref = oc.kcenters(X, od.euclidean, n_clusters=70, trace=trace)
+    got = kcenters.kcenters(X, "euclidean", n_clusters=70)
+    assert [int(c) for c in got.center_indices] == [int(c) for c in ref.center_indices]
+    assert_array_equal(got.assignments, ref.assignments)
+    assert_array_equal(got.distances, ref.distances)
+    # cutoff between the 40th and 41st max-min-distance (inside the second batch of 32), at
+    # the 32nd (batch boundary) and at the 1st
+    for stop_after in (40, 32, 1):
+        cut = 0.5 * (trace[stop_after - 1][1] + trace[stop_after][1]) \
+            if trace[stop_after - 1][1] > trace[stop_after][1] else trace[stop_after - 1][1]
+        ref_c = oc.kcenters(X, od.euclidean, dist_cutoff=cut)
+        got_c = kcenters.kcenters(X, "euclidean", dist_cutoff=cut)
+        assert [int(c) for c in got_c.center_indices] == [int(c) for c in ref_c.center_indices]
+        assert_array_equal(got_c.assignments, ref_c.assignments)
+        assert_array_equal(got_c.distances, ref_c.distances)
+    ref_b = oc.kcenters(X, od.manhattan, n_clusters=45, dist_cutoff=float(trace[50][1]))
+    got_b = kcenters.kcenters(X, "manhattan", n_clusters=45, dist_cutoff=float(trace[50][1]))
+    assert [int(c) for c in got_b.center_indices] == [int(c) for c in ref_b.center_indices]
+    assert_array_equal(got_b.distances, ref_b.distances)
+
+
+def test_multi_iteration_kernel_edge_cases(cuda):
+    """More clusters requested than rows (every row becomes a centre, then the stop rule fires
+    on maxdist == 0), duplicate rows (exact ties -> first occurrence), a warm start
+    (init_centers: centre ids continue after the existing ones), and a tiny shard whose grid is
+    a single block."""
+    from enspara_b200.cluster import kcenters
+    from oracle import cluster as oc
+    from oracle import distances as od
+    rs = np.random.RandomState(5)
+    base = rs.rand(300, 64).astype(np.float32)
+    for X, kw in ((base[:9], dict(n_clusters=50)),
+                  (np.concatenate([base, base, base[:50]]), dict(n_clusters=120)),
+                  (base, dict(n_clusters=40, init_centers=base[[7, 100, 250]])),
+                  (base[:33], dict(dist_cutoff=2.5))):
+        ref = oc.kcenters(X, od.euclidean, **kw)
+        got = kcenters.kcenters(X, "euclidean", **kw)
+        assert [int(c) for c in got.center_indices] == [int(c) for c in ref.center_indices], kw
+        assert_array_equal(got.assignments, ref.assignments)
+        assert_array_equal(got.distances, ref.distances)
+
+
+def test_multi_and_single_launches_mix(cuda):
+    """The engine queues batches; a batch of one step takes the single-launch kernel, longer
+    ones the persistent kernel.  Driving the engine with batch sizes 1, 5, 1, 32, 3 must give
+    the run a plain call gives."""
+    import torch
+    from enspara_b200 import synth
+    from enspara_b200.cluster import kcenters as kc
+    from enspara_b200.cluster._engine import KCentersEngine
+    X = synth.device_features(30_000, 64, seed=4)
+    want = kc.kcenters(X, "euclidean", n_clusters=42)
+    eng = KCentersEngine(X, "euclidean", kc._SingleComm())
+    eng._ensure_center_list(64)
+    eng.seed(0)
+    for b in (1, 5, 1, 32, 3):
+        eng.step(1 << 30, 0.0, b)
+    st = eng.read_state()
+    assert st.n_centers == 42 and not st.done
+    got_c = eng.center_list[:42].cpu().numpy().tolist()
+    assert got_c == [int(c) for c in want.center_indices]
+    a, d = eng.results_host()
+    assert_array_equal(a, want.assignments)
+    assert_array_equal(d, want.distances)
+    # a limit reached inside a batch: the remaining launches are no-ops
+    eng2 = KCentersEngine(X, "euclidean", kc._SingleComm())
+    eng2._ensure_center_list(64)
+    eng2.seed(0)
+    eng2.step(10, 0.0, 25)
+    st2 = eng2.read_state()
+    assert st2.n_centers == 10 and st2.done == 1
+    eng2.step(10, 0.0, 4)
+    st3 = eng2.read_state()
+    assert st3.n_centers == 10 and st3.done == 1 and st3.n_noop >= st2.n_noop + 4
+    assert eng2.center_list[:10].cpu().numpy().tolist() == got_c[:10]
+    torch.cuda.synchronize()
