@@ -65,6 +65,10 @@ SIGNATURES = {
                                          _vp, _vp]),
     "eb_rmsd_assign": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _int,
                               _int, _vp]),
+    "eb_rmsd_assign_dev": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _i32, _vp, _i64, _vp, _vp,
+                                  _int, _int, _vp, _vp]),
+    "eb_rmsd_assign_tc_dev": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _i32, _dbl, _vp, _int, _vp,
+                                     _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp]),
     "eb_tc_scratch_bytes": (_sz, [_i64, _int, _i32]),
     "eb_rmsd_assign_tc": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _i32, _dbl, _vp, _int, _vp, _vp,
                                  _vp, _vp, _vp, _int, _vp]),

@@ -105,7 +105,7 @@ def centers_to_device(metric, cluster_centers, like):
 
 
 def assign_device(metric, data, centers, frame_idx=None, out_dist=None, out_assign=None,
-                  accumulate=False, scatter=False, n_idx=None, k=None):
+                  accumulate=False, scatter=False, n_idx=None, k=None, n_dev=None):
     """Nearest-centre pass on the device.  Returns (dist tensor, assign int32 tensor).
     ``scatter``: out arrays are full length and frame f's result goes to position f."""
     n = len(data)
@@ -119,9 +119,9 @@ def assign_device(metric, data, centers, frame_idx=None, out_dist=None, out_assi
     if m == 0 or k == 0:
         return out_dist, out_assign
     if metric.is_rmsd:
-        _lib.call("eb_rmsd_assign", ptr(data.xyz), ptr(data.traces), n, data.n_atoms,
+        _lib.call("eb_rmsd_assign_dev", ptr(data.xyz), ptr(data.traces), n, data.n_atoms,
                   ptr(centers.xyz), ptr(centers.traces), k, ptr(frame_idx), m, ptr(out_dist),
-                  ptr(out_assign), int(accumulate), int(scatter), stream_ptr())
+                  ptr(out_assign), int(accumulate), int(scatter), ptr(n_dev), stream_ptr())
     else:
         from ._engine import _lib_metric
         _lib.call("eb_feat_assign", ptr(data.X), n, data.n_features, data.dt,
@@ -238,12 +238,20 @@ def tc_applicable(metric, data, k):
 
 
 def assign_device_tc(metric, data, centers, k=None, stats=None, frame_idx=None, n_idx=None,
-                     out_dist=None, out_assign=None, scatter=False, workspace=None):
+                     out_dist=None, out_assign=None, scatter=False, workspace=None,
+                     n_dev=None, defer=False):
     """Nearest-centre pass through the tcgen05 screen + exact re-score (csrc/eb_tc_screen.cu).
     Same result as ``assign_device`` (the exact path decides).  ``frame_idx`` (device int64)
     restricts the pass to a subset; with ``scatter`` the full-length ``out_*`` arrays receive
     frame f's result at position f (PAM's re-assignment of X[dst_up_assig_this],
-    kmedoids.py:666-667).  ``workspace``: dict reused between calls (scratch buffers)."""
+    kmedoids.py:666-667).  ``workspace``: dict reused between calls (scratch buffers).
+
+    ``n_dev`` (device int32/int64 tensor, first element read as int32): the real subset size
+    when only the device knows it; ``n_idx`` is then the host's upper bound.  ``defer=True``
+    (single-chunk subsets only) returns without synchronising: the third return value is a
+    device int32 counter of frames whose candidate lists overflowed -- the caller reads it with
+    its next read-back and, if non-zero, calls ``assign_device`` for the subset (the exact
+    fallback this function otherwise does itself)."""
     n = len(data)
     k = len(centers) if k is None else int(k)
     dev = data.xyz.device
@@ -254,7 +262,7 @@ def assign_device_tc(metric, data, centers, k=None, stats=None, frame_idx=None, 
         out_assign = torch.zeros((m,), dtype=torch.int32, device=dev)
         scatter = False
     if m == 0 or k == 0:
-        return out_dist, out_assign
+        return (out_dist, out_assign, None) if defer else (out_dist, out_assign)
     ws = workspace if workspace is not None else {}
     chunk = min(m, TC_CHUNK_FRAMES)
     need = int(lib.eb_tc_scratch_bytes(chunk, data.n_atoms, k))
@@ -265,6 +273,19 @@ def assign_device_tc(metric, data, centers, k=None, stats=None, frame_idx=None, 
         ws["cand"] = torch.empty(m + m // 4 + 128, dtype=torch.int32, device=dev)
     scratch, cand = ws["scratch"], ws["cand"][:m]
     kappa = tc_kappa(data.a_pad)
+    if defer:
+        if frame_idx is None or m > chunk:
+            raise ValueError("defer=True needs a single-chunk frame subset")
+        if ws.get("ovf") is None:
+            ws["ovf"] = torch.zeros(1, dtype=torch.int32, device=dev)
+        ws["ovf"].zero_()
+        od = out_dist
+        oa = out_assign
+        _lib.call("eb_rmsd_assign_tc_dev", ptr(data.xyz), ptr(data.traces), m, data.n_atoms,
+                  ptr(centers.xyz), ptr(centers.traces), k, float(kappa), ptr(frame_idx),
+                  int(scatter), ptr(od), ptr(oa), ptr(cand), ptr(scratch), None, 1, ptr(n_dev),
+                  ptr(ws["ovf"]), stream_ptr())
+        return out_dist, out_assign, ws["ovf"]
     for lo in range(0, m, chunk):
         hi = min(m, lo + chunk)
         if frame_idx is None:

@@ -72,6 +72,13 @@ class PamEngine:
         # stay with their medoid are not read; the sweep's result is unchanged
         self.prune = self.is_rmsd and self.k >= 2
         self.cc = torch.zeros(max(self.k, 1), dtype=torch.float32, device=dev)
+        self.counts_by_rank = None
+        self._proposals_done = 0
+        # pinned landing zone of the one read-back per proposal: [cost], [proposal, n_ambig],
+        # [overflowed frames]
+        self._pin_d = torch.zeros(1, dtype=torch.float64).pin_memory()
+        self._pin_i = torch.zeros(2, dtype=torch.int64).pin_memory()
+        self._pin_o = torch.zeros(1, dtype=torch.int32).pin_memory()
 
     # -- helpers -------------------------------------------------------------------------
     def _to_dev(self, arr, dtype):
@@ -146,6 +153,23 @@ class PamEngine:
         self.comm.all_reduce_sum(t)
         return float(t.cpu()[0])
 
+    def _sumsq_with(self, vec, scal_i, ovf):
+        """Global sum of squares of ``vec`` plus the proposal's integer scalars and the screen's
+        overflow counter, all fetched with ONE stream synchronisation."""
+        _lib.call("eb_sum_squares", ptr(vec), self.n, int(not self.is_rmsd), ptr(self.scal_d),
+                  ptr(self.scratch), stream_ptr())
+        t = self.scal_d
+        if self.shard.size > 1:
+            t = self.scal_d.clone()
+            self.comm.all_reduce_sum(t)
+        self._pin_d.copy_(t, non_blocking=True)
+        self._pin_i.copy_(scal_i, non_blocking=True)
+        if ovf is not None:
+            self._pin_o.copy_(ovf, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return (float(self._pin_d[0]), self._pin_i.clone(),
+                int(self._pin_o[0]) if ovf is not None else 0)
+
     def _refresh_counts(self):
         """Member counts of every cluster on every rank (len(np.where(assignments == cid)[0]),
         kmedoids.py:611).  Assignments only change when a proposal is accepted, so the counts
@@ -218,8 +242,7 @@ class PamEngine:
                 prof[name] = prof.get(name, 0.0) + now - t0
             return now
         t = tick(None, 0.0)
-        if proposals is None:
-            self._refresh_counts()
+        self._refresh_counts()
         t = tick("counts", t)
         for cid in range(self.k if max_proposals is None else min(self.k, max_proposals)):
             # ---- proposal (kmedoids.py:616-628, 482-517) -------------------------------
@@ -266,33 +289,68 @@ class PamEngine:
                       int(not self.is_rmsd), cid, ptr(self.new_dist), ptr(self.new_assign),
                       ptr(self.ambig_idx), ptr(self.scal_i[1:]), stream_ptr())
             self.scal_i[:1].copy_(self.prop_idx)
-            scal = self.scal_i.cpu()
-            n_ambig = int(scal[1])
-            if prop_global is None:
-                prop_global = int(scal[0])
-
-            t = tick("classify+readback", t)
             # ---- ambiguous frames against all medoids, proposal in slot cid (:660-670) --
             self._slot_copy(self.saved, 0, self.medoids, cid)
             self._slot_copy(self.medoids, cid, self.prop, 0)
-            if n_ambig > 0:
-                if self.use_tc and n_ambig * self.k >= self.TC_MIN_PAIRS:
-                    # tensor-core screen + exact re-score: same result as the exact kernel
-                    _ops.assign_device_tc(self.metric, self.data, self.medoids, k=self.k,
-                                          frame_idx=self.ambig_idx, n_idx=n_ambig,
-                                          out_dist=self.new_dist, out_assign=self.new_assign,
-                                          scatter=True, workspace=self._tc_ws)
-                else:
+            self._proposals_done += 1
+            # RMSD: the size of the ambiguous subset stays on the device (every ambiguous
+            # frame is a member of cluster cid, so the cached member count bounds it); the
+            # host reads it back together with the trial cost -- ONE synchronisation per
+            # proposal.  Every TC_AUDIT_EVERY-th proposal takes the synchronous path, which
+            # also runs the screen's audit.
+            deferred = (self.is_rmsd and self.counts_by_rank is not None
+                        and (self._proposals_done % _ops.TC_AUDIT_EVERY != 0
+                             or _ops._audit_level() == 0) and prof is None)
+            ovf = None
+            if deferred:
+                m_max = int(self._member_counts(cid)[sh.rank])
+                if m_max > 0:
+                    if self.use_tc and m_max * self.k >= self.TC_MIN_PAIRS \
+                            and m_max <= _ops.TC_CHUNK_FRAMES:
+                        _, _, ovf = _ops.assign_device_tc(
+                            self.metric, self.data, self.medoids, k=self.k,
+                            frame_idx=self.ambig_idx, n_idx=m_max, out_dist=self.new_dist,
+                            out_assign=self.new_assign, scatter=True, workspace=self._tc_ws,
+                            n_dev=self.scal_i[1:], defer=True)
+                    else:
+                        _ops.assign_device(self.metric, self.data, self.medoids,
+                                           frame_idx=self.ambig_idx, n_idx=m_max,
+                                           out_dist=self.new_dist, out_assign=self.new_assign,
+                                           accumulate=False, scatter=True, k=self.k,
+                                           n_dev=self.scal_i[1:])
+                new_num, scal, n_ovf = self._sumsq_with(self.new_dist, self.scal_i, ovf)
+                n_ambig = int(scal[1])
+                if n_ovf > 0:
+                    # a candidate list overflowed: exact kernel for the subset, cost again
                     _ops.assign_device(self.metric, self.data, self.medoids,
                                        frame_idx=self.ambig_idx, n_idx=n_ambig,
                                        out_dist=self.new_dist, out_assign=self.new_assign,
                                        accumulate=False, scatter=True, k=self.k)
-
-            t = tick("subset_assign", t)
+                    new_num = self._sumsq(self.new_dist)
+            else:
+                scal = self.scal_i.cpu()
+                n_ambig = int(scal[1])
+                t = tick("classify+readback", t)
+                if n_ambig > 0:
+                    if self.use_tc and n_ambig * self.k >= self.TC_MIN_PAIRS:
+                        # tensor-core screen + exact re-score: same result as the exact kernel
+                        _ops.assign_device_tc(self.metric, self.data, self.medoids, k=self.k,
+                                              frame_idx=self.ambig_idx, n_idx=n_ambig,
+                                              out_dist=self.new_dist,
+                                              out_assign=self.new_assign, scatter=True,
+                                              workspace=self._tc_ws)
+                    else:
+                        _ops.assign_device(self.metric, self.data, self.medoids,
+                                           frame_idx=self.ambig_idx, n_idx=n_ambig,
+                                           out_dist=self.new_dist, out_assign=self.new_assign,
+                                           accumulate=False, scatter=True, k=self.k)
+                t = tick("subset_assign", t)
+                new_num = self._sumsq(self.new_dist)
+            if prop_global is None:
+                prop_global = int(scal[0])
             if prof is not None:
                 prof["n_ambig"] = prof.get("n_ambig", 0) + n_ambig
             # ---- accept / reject on mean-square cost (kmedoids.py:680-694) -----------------
-            new_num = self._sumsq(self.new_dist)
             old_cost = self.cost_num / self.n_global
             new_cost = new_num / self.n_global
             accepted = new_cost < old_cost
@@ -304,7 +362,7 @@ class PamEngine:
                 self.cost_num = new_num
                 self.medoid_global[cid] = prop_global
                 acceptances += 1
-                if proposals is None and cid + 1 < self.k:
+                if cid + 1 < self.k:
                     self._refresh_counts()
             else:
                 self._slot_copy(self.medoids, cid, self.saved, 0)

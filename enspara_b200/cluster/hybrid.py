@@ -56,9 +56,10 @@ def hybrid(X, distance_method, n_iters=5, n_clusters=np.inf, dist_cutoff=0,
     if not hasattr(data, "host") or data.host is None:
         data.host = X if X is not data else None
 
-    result = kcenters.kcenters(
+    result, kc_engine = kcenters.kcenters(
         data, metric, n_clusters=n_clusters, dist_cutoff=dist_cutoff,
-        init_centers=init_centers, random_first_center=random_first_center, mpi_mode=mpi_mode)
+        init_centers=init_centers, random_first_center=random_first_center, mpi_mode=mpi_mode,
+        _return_engine=True)
     if X is not data and not mpi_mode:
         # centres are slices of the caller's object, like kcenters.py:283
         result = result._replace(centers=[X[int(i)] for i in result.center_indices])
@@ -68,7 +69,9 @@ def hybrid(X, distance_method, n_iters=5, n_clusters=np.inf, dist_cutoff=0,
         cio.write_intermediate(result, args, lengths, "kcenters")
 
     if n_iters > 0:
+        # the k-centers state goes to the PAM engine as DEVICE tensors (same values as the host
+        # copies in `result`; no device -> host -> device round trip between the phases)
         return kmedoids._kmedoids_iterations(
-            X, metric, n_iters, result.center_indices, result.assignments, result.distances,
+            X, metric, n_iters, result.center_indices, kc_engine.assign, kc_engine.dist,
             args=args, lengths=lengths, random_state=random_state, _data=data)
     return result

@@ -457,6 +457,7 @@ k_kcenters_multi_feat(const T *__restrict__ X, long n, long F, long frame_offset
 
     int it = 0;
     bool stopped = false;
+    unsigned long long sync_ns = 0, t_body_end = 0;
     double win_d = 0.0;        // distance / global index of the winner examined last
     int64_t win_i = -1;
     for (; it < n_steps; ++it) {
@@ -501,7 +502,11 @@ k_kcenters_multi_feat(const T *__restrict__ X, long n, long F, long frame_offset
             break;
         }
         for (long j = threadIdx.x; j < F; j += blockDim.x) y_sh[j] = src[j];
-        if (blockIdx.x == 0 && threadIdx.x == 0) center_list[k] = win_i;
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            center_list[k] = win_i;
+            // diagnostic: time block 0 spends between two bodies (arg-max barrier + prologue)
+            if (it > 0) sync_ns += globaltimer_ns() - t_body_end;
+        }
         __syncthreads();
 
         // ---- body: every row once, strict '<' update, arg-max --------------------------------
@@ -540,6 +545,7 @@ k_kcenters_multi_feat(const T *__restrict__ X, long n, long F, long frame_offset
             }
         }
         // ---- shard arg-max: per-block partial, grid barrier ------------------------------------
+        if (blockIdx.x == 0 && threadIdx.x == 0) t_body_end = globaltimer_ns();
         block_argmax(best_d, best_i, ss->red);
         if (threadIdx.x == 0) {
             Partial *pp = partials + (size_t)(it & 1) * G;
@@ -614,6 +620,7 @@ k_kcenters_multi_feat(const T *__restrict__ X, long n, long F, long frame_offset
             state->maxdist = win_d;
         }
         state->blocks_done = 0;
+        state->wait_ns += (long long)sync_ns;
         __threadfence();
     }
     (void)rec_bytes;

@@ -67,8 +67,10 @@ __global__ void __launch_bounds__(kAsgThreads)
 k_rmsd_assign(const float *__restrict__ xyz, const double *__restrict__ traces, long n, int A,
               int A_pad, const float *__restrict__ centers, const double *__restrict__ ctraces,
               int k, const int64_t *__restrict__ frame_idx, long m, float *out_dist,
-              int *out_assign, int accumulate, int scatter, int TC)
+              int *out_assign, int accumulate, int scatter, int TC,
+              const int *__restrict__ m_dev)
 {
+    if (m_dev) m = min(m, (long)__ldg(m_dev));   // device-side subset size (<= the host's m)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *sums = reinterpret_cast<double *>(smem_raw);                 // [warps][32][9]
     double *ctr_trace = sums + kAsgWarps * 32 * 9;                       // [TC]
@@ -180,6 +182,20 @@ extern "C" int eb_rmsd_assign(const float *xyz_soa, const double *traces, int64_
                               const int64_t *frame_idx, int64_t n_idx, float *out_dist,
                               int32_t *out_assign, int accumulate, int scatter, void *stream)
 {
+    return eb_rmsd_assign_dev(xyz_soa, traces, n, n_atoms, centers_soa, center_traces, k,
+                              frame_idx, n_idx, out_dist, out_assign, accumulate, scatter,
+                              nullptr, stream);
+}
+
+// n_idx is the host's upper bound of the subset size, *n_idx_dev (optional, <= n_idx) the real
+// one, known only on the device (PAM's ambiguous frames).
+extern "C" int eb_rmsd_assign_dev(const float *xyz_soa, const double *traces, int64_t n,
+                                  int n_atoms, const float *centers_soa,
+                                  const double *center_traces, int32_t k,
+                                  const int64_t *frame_idx, int64_t n_idx, float *out_dist,
+                                  int32_t *out_assign, int accumulate, int scatter,
+                                  const int32_t *n_idx_dev, void *stream)
+{
     EB_CHECK_ARG(n >= 0 && n_atoms > 0 && k >= 0 && n_idx >= 0, "rmsd_assign: bad shape");
     const long m = frame_idx ? n_idx : n;
     if (m == 0 || k == 0) return EB_OK;
@@ -209,7 +225,7 @@ extern "C" int eb_rmsd_assign(const float *xyz_soa, const double *traces, int64_
     if (blocks > (long)per_sm * sm_count()) blocks = (long)per_sm * sm_count();
     k_rmsd_assign<<<(int)blocks, kAsgThreads, smem, (cudaStream_t)stream>>>(
         xyz_soa, traces, n, n_atoms, A_pad, centers_soa, center_traces, k, frame_idx, m, out_dist,
-        out_assign, accumulate, scatter, (int)TC);
+        out_assign, accumulate, scatter, (int)TC, n_idx_dev);
     EB_LAUNCH_CHECK();
     return EB_OK;
 }

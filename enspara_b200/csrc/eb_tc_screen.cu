@@ -82,8 +82,12 @@ __device__ __forceinline__ void split_f16x2(float x, __half &h1, __half &h2, boo
 
 __global__ void __launch_bounds__(256)
 k_pack_f16x2(const float *__restrict__ x, long rows_total, int A_pad, int RT, int S, long n_tiles,
-             const int64_t *__restrict__ row_idx, unsigned char *__restrict__ img, int *overflow)
+             const int64_t *__restrict__ row_idx, unsigned char *__restrict__ img, int *overflow,
+             const int *__restrict__ n_items_dev)
 {
+    // optional device-side item count (PAM: the number of ambiguous frames is only known on
+    // the device): rows of items beyond it are zero-filled and their row_idx is never read
+    if (n_items_dev) rows_total = min(rows_total, (long)S * (long)__ldg(n_items_dev));
     const int Qs = A_pad >> 3;               // 8-atom chunks per source row (A_pad % 8 == 0)
     const int KB = (A_pad + BK - 1) / BK;    // k-blocks of the image (zero-padded to 32 atoms)
     const int Q = KB * 4;                    // 16-byte chunks per image row
@@ -231,10 +235,11 @@ k_tc_screen(const unsigned char *__restrict__ a_img, const unsigned char *__rest
             const double *__restrict__ traces, const double *__restrict__ ctraces, long n, int k,
             int n_atoms, int A_pad, double kappa, float *dbg, int *cand_count, int *cand_list,
             float *cand_bound, float *cand_umin, int n_seg, const int64_t *__restrict__ frame_idx,
-            int MAX_CAND)
+            int MAX_CAND, const int *__restrict__ n_dev)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *tiles = smem_raw;
+    if (n_dev) n = min(n, (long)__ldg(n_dev));   // device-side frame count (<= the host's n)
     Smem *sm = reinterpret_cast<Smem *>(tiles + (size_t)STAGES * STAGE_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -519,9 +524,10 @@ k_rescore(const float *__restrict__ xyz, const double *__restrict__ traces, long
           const float *__restrict__ cand_bound, const float *__restrict__ cand_umin, int n_seg,
           float *out_dist, int *out_assign, int *frame_flag,
           const int64_t *__restrict__ frame_idx, int scatter, int MAX_CAND,
-          const int *__restrict__ f16_overflow)
+          const int *__restrict__ f16_overflow, const int *__restrict__ n_dev, int *ovf_count)
 {
     extern __shared__ __align__(16) unsigned char rs_smem[];
+    if (n_dev) n = min(n, (long)__ldg(n_dev));
     const int list_cap = n_seg * MAX_CAND;
     int *cl_all = reinterpret_cast<int *>(rs_smem);                       // [RS_GROUPS][list_cap]
     const int lane = threadIdx.x & 31, g = lane >> 3, l8 = lane & 7;
@@ -622,6 +628,7 @@ k_rescore(const float *__restrict__ xyz, const double *__restrict__ traces, long
         if (valid && l8 == 0) {
             if (overflow || cnt_g == 0) {
                 frame_flag[f] = -1;  // the host sends this frame through the exact kernel
+                if (ovf_count) atomicAdd(ovf_count, 1);
             } else {
                 frame_flag[f] = cnt_g;
                 const long o = scatter ? src : f;
@@ -711,6 +718,22 @@ int eb_rmsd_assign_tc(const float *xyz_soa, const double *traces, int64_t n, int
                       int32_t *out_assign, int32_t *cand_count, void *scratch, float *dbg,
                       int mode, void *stream)
 {
+    return eb_rmsd_assign_tc_dev(xyz_soa, traces, n, n_atoms, centers_soa, center_traces, k,
+                                 kappa, frame_idx, scatter, out_dist, out_assign, cand_count,
+                                 scratch, dbg, mode, nullptr, nullptr, stream);
+}
+
+// The same pass with the number of frames known only on the DEVICE: n is the host's upper bound
+// (grids, scratch and list layout are sized by it), *n_dev (<= n) the real count; positions
+// beyond it are neither read nor written.  overflow_count (optional) is incremented once per
+// frame whose candidate lists overflowed (cand_count = -1), so that a caller can defer the
+// exact fallback to its next read-back instead of synchronising here.
+int eb_rmsd_assign_tc_dev(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
+                          const float *centers_soa, const double *center_traces, int32_t k,
+                          double kappa, const int64_t *frame_idx, int scatter, float *out_dist,
+                          int32_t *out_assign, int32_t *cand_count, void *scratch, float *dbg,
+                          int mode, const int32_t *n_dev, int32_t *overflow_count, void *stream)
+{
     EB_CHECK_ARG(n >= 0 && n_atoms > 0 && k >= 0, "rmsd_assign_tc: bad shape");
     if (n == 0 || k == 0) return EB_OK;
     EB_CHECK_ARG(xyz_soa && traces && centers_soa && center_traces && scratch,
@@ -744,14 +767,14 @@ int eb_rmsd_assign_tc(const float *xyz_soa, const double *traces, int64_t n, int
         long blocks = (total + 255) / 256;
         if (blocks > 32L * sm_count()) blocks = 32L * sm_count();
         tc::k_pack_f16x2<<<(int)blocks, 256, 0, s>>>(xyz_soa, 3L * n, A_pad, tc::BM, 3, n_ft,
-                                                     frame_idx, a_img, f16_overflow);
+                                                     frame_idx, a_img, f16_overflow, n_dev);
         EB_LAUNCH_CHECK();
         const long b_tiles = n_ct_total;
         total = b_tiles * tc::BN * (long)(A_img / 8);
         blocks = (total + 255) / 256;
         if (blocks > 32L * sm_count()) blocks = 32L * sm_count();
         tc::k_pack_f16x2<<<(int)blocks, 256, 0, s>>>(centers_soa, 3L * k, A_pad, tc::BN, 1,
-                                                     b_tiles, nullptr, b_img, f16_overflow);
+                                                     b_tiles, nullptr, b_img, f16_overflow, nullptr);
         EB_LAUNCH_CHECK();
     }
     const size_t smem = (size_t)tc::STAGES * tc::STAGE_BYTES + sizeof(tc::Smem) + 1024;
@@ -764,7 +787,7 @@ int eb_rmsd_assign_tc(const float *xyz_soa, const double *traces, int64_t n, int
         tc::k_tc_screen<0><<<grid, tc::THREADS, smem, s>>>(a_img, b_img, traces,
                                                            center_traces, n, k, n_atoms, A_pad,
                                                            kappa, dbg, nullptr, nullptr, nullptr,
-                                                           nullptr, n_seg, frame_idx, 8);
+                                                           nullptr, n_seg, frame_idx, 8, n_dev);
         EB_LAUNCH_CHECK();
         return EB_OK;
     }
@@ -774,7 +797,7 @@ int eb_rmsd_assign_tc(const float *xyz_soa, const double *traces, int64_t n, int
         tc::k_tc_screen<2><<<grid, tc::THREADS, smem, s>>>(a_img, b_img, traces,
                                                            center_traces, n, k, n_atoms, A_pad,
                                                            kappa, dbg, nullptr, nullptr, nullptr,
-                                                           nullptr, n_seg, frame_idx, 8);
+                                                           nullptr, n_seg, frame_idx, 8, n_dev);
         EB_LAUNCH_CHECK();
         return EB_OK;
     }
@@ -784,7 +807,8 @@ int eb_rmsd_assign_tc(const float *xyz_soa, const double *traces, int64_t n, int
     tc::k_tc_screen<1><<<grid, tc::THREADS, smem, s>>>(a_img, b_img, traces,
                                                        center_traces, n, k, n_atoms, A_pad, kappa,
                                                        nullptr, seg_count, cand_list, cand_bound,
-                                                       cand_umin, n_seg, frame_idx, max_cand);
+                                                       cand_umin, n_seg, frame_idx, max_cand,
+                                                       n_dev);
     EB_LAUNCH_CHECK();
     {
         const size_t rs_smem = align16(sizeof(int) * tc::RS_GROUPS * n_lists * max_cand);
@@ -796,7 +820,7 @@ int eb_rmsd_assign_tc(const float *xyz_soa, const double *traces, int64_t n, int
         tc::k_rescore<<<(int)blocks, tc::RS_THREADS, rs_smem, s>>>(
             xyz_soa, traces, n, n_atoms, A_pad, centers_soa, center_traces, seg_count, cand_list,
             cand_bound, cand_umin, (int)n_lists, out_dist, out_assign, cand_count, frame_idx,
-            scatter, max_cand, f16_overflow);
+            scatter, max_cand, f16_overflow, n_dev, overflow_count);
         EB_LAUNCH_CHECK();
     }
     return EB_OK;
@@ -830,7 +854,7 @@ int eb_rmsd_score_lists(const float *xyz_soa, const double *traces, int64_t n_po
     tc::k_rescore<<<(int)blocks, tc::RS_THREADS, rs_smem, (cudaStream_t)stream>>>(
         xyz_soa, traces, n_pos, n_atoms, rmsd_apad(n_atoms), centers_soa, center_traces,
         cand_count, cand_list, bound_lo, bound_up, 1, out_dist, out_assign, frame_flag, frame_idx,
-        0, list_len, zero_flag);
+        0, list_len, zero_flag, nullptr, nullptr);
     EB_LAUNCH_CHECK();
     return EB_OK;
 }

@@ -178,6 +178,12 @@ int eb_rmsd_assign(const float *xyz_soa, const double *traces, int64_t n, int n_
                    const float *centers_soa, const double *center_traces, int32_t k,
                    const int64_t *frame_idx, int64_t n_idx, float *out_dist,
                    int32_t *out_assign, int accumulate, int scatter, void *stream);
+/* n_idx = host upper bound of the subset size, *n_idx_dev (int32, optional) the real one. */
+int eb_rmsd_assign_dev(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
+                       const float *centers_soa, const double *center_traces, int32_t k,
+                       const int64_t *frame_idx, int64_t n_idx, float *out_dist,
+                       int32_t *out_assign, int accumulate, int scatter,
+                       const int32_t *n_idx_dev, void *stream);
 
 size_t eb_feat_record_bytes(int64_t n_features, int dtype);
 /* ---- K2: fused k-centers step, feature vectors (libdist.pyx:100-145) -------------------
@@ -227,6 +233,17 @@ int eb_rmsd_assign_tc(const float *xyz_soa, const double *traces, int64_t n, int
                       double kappa, const int64_t *frame_idx, int scatter, float *out_dist,
                       int32_t *out_assign, int32_t *cand_count, void *scratch, float *dbg,
                       int mode, void *stream);
+/* The same pass when the number of frames is known only on the DEVICE (PAM: the ambiguous
+ * subset is counted by eb_pam_classify): n is the host's upper bound (grids, scratch and list
+ * layout are sized by it), *n_dev (int32, <= n, optional) the real count -- positions beyond it
+ * are neither read nor written.  overflow_count (optional) is incremented once per frame whose
+ * candidate lists overflowed, so the caller can defer the exact fallback to its next read-back
+ * instead of synchronising after every pass. */
+int eb_rmsd_assign_tc_dev(const float *xyz_soa, const double *traces, int64_t n, int n_atoms,
+                          const float *centers_soa, const double *center_traces, int32_t k,
+                          double kappa, const int64_t *frame_idx, int scatter, float *out_dist,
+                          int32_t *out_assign, int32_t *cand_count, void *scratch, float *dbg,
+                          int mode, const int32_t *n_dev, int32_t *overflow_count, void *stream);
 /* Exact scoring of explicit per-position centre lists (the re-score stage on its own; exact
  * float64 inner products, lowest centre index on ties like cluster/util.py:201): position p
  * covers frame frame_idx[p] (or p when NULL) and the centres cand_list[p*list_len ..

@@ -26,9 +26,12 @@ def bench_k2(n=1_000_000, F=64, k=200):
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         evs = n * k / (ms * 1e-3)
-        print("K2 %s n=%d F=%d k=%d: %.1f us/iter %.2f G evals/s %.0f GB/s (%.1f%% of 6543)"
+        st = eng.read_state()
+        print("K2 %s n=%d F=%d k=%d: %.1f us/iter %.2f G evals/s %.0f GB/s (%.1f%% of 6543); "
+              "block 0 between two bodies: %.2f us/iter"
               % (metric, n, F, k, 1e3 * ms / k, evs / 1e9, evs * (4 * F + 8) / 1e9,
-                 100 * evs * (4 * F + 8) / 1e9 / 6543.1), flush=True)
+                 100 * evs * (4 * F + 8) / 1e9 / 6543.1, 1e-3 * st.wait_ns / max(1, k - 1)),
+              flush=True)
 
 
 def bench_k3(n=200_000, A=500, k=1000):
