@@ -555,6 +555,7 @@ k_kcenters_multi_feat(const T *__restrict__ X, long n, long F, long frame_offset
             atomicAdd(gbar, 1ull);
             const unsigned long long target = gbase + (unsigned long long)(it + 1) * G;
             while (ld_acquire_gpu_u64(gbar) < target) {
+                __nanosleep(32);   // back off: hundreds of pollers on one line slow the arrivals
             }
         }
         __syncthreads();

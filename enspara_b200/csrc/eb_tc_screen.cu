@@ -40,7 +40,8 @@ namespace tc {
 
 constexpr int BM = 128;                  // frames per tile  (= TMEM lanes)
 constexpr int NC = 48;                   // centres per tile
-constexpr int BN = 3 * NC;               // B rows per tile: (centre, coordinate)
+constexpr int BN_USED = 3 * NC;          // B rows per tile that carry (centre, coordinate) ...
+constexpr int BN = 144;                  // ... padded with zero rows to the UMMA N step of 16
 constexpr int BK = 32;                   // atoms per stage: 64-byte rows of FP16
 constexpr int STAGES = 3;
 constexpr int A_TILE = BM * BK * 2;      // 8192
@@ -49,17 +50,30 @@ constexpr int STAGE_BYTES = 6 * A_TILE + 2 * B_TILE;  // {h1,h2} x 3 coords of A
 constexpr float kOperandScale = 256.0f;               // x*2^8 before the FP16 split
 constexpr float kAccumUnscale = 1.0f / 65536.0f;      // accumulators hold 2^16 * M
 constexpr float kF16Limit = 65000.0f;                 // |x*2^8| beyond this cannot be split
-constexpr int TMEM_COLS = 512;           // 3 accumulators x 144 columns = 432 -> power of two
-constexpr int THREADS = 64 + 128 * 2;  // producer, MMA, 8 epilogue warps
+// Tile shape.  tcgen05 operands are read from shared memory at 128 B/clk/SM: an M=128 x N MMA
+// of 16 FP16 atoms takes max(N/2, (4096 + 32 N) / 128) clocks, so N = 144 (72 clk for 8.6 KB)
+// is tensor-bound while N = 80 -- the widest tile that leaves TMEM room for a SECOND accumulator
+// set (2 x 3 x 80 = 480 columns) -- is operand-read-bound: measured, the MMA stream of the
+// 262144 x 1008 x 500 pass takes 4.97 ms at N = 144 and 7.05 ms at N = 80.  So: one accumulator
+// set of 3 x 144 columns, and the overlap comes from draining it early instead -- twelve
+// epilogue warps (three per TMEM lane quarter) each own 16 centres = two groups of 8; a warp
+// pulls a group's 72 values into registers, and after the LAST group's load it hands TMEM back,
+// so the next tile's MMAs run under the second half of the QCP arithmetic.
+constexpr int ACC_SETS = (2 * 3 * BN <= 512) ? 2 : 1;
+constexpr int ACC_COLS = 3 * BN;         // columns of one accumulator set
+constexpr int TMEM_COLS = 512;
+constexpr int EPI_PARTS = 3;   // epilogue warps per TMEM lane quarter
+constexpr int EPI_WARPS = 4 * EPI_PARTS;
+constexpr int GROUPS_PER_WARP = NC / 8 / EPI_PARTS;   // groups of 8 centres (24 columns) per warp
+constexpr int THREADS = 64 + 32 * EPI_WARPS;  // producer, MMA, 12 epilogue warps
 constexpr int CAND_BUDGET = 512;  // candidate entries per frame, shared out over its lists
 constexpr int MIN_CAND = 8;       // ... but never fewer than this per list
 constexpr int DEF_SEG = 4;     // centre segments: CTAs sharing a frame tile hit it in L2
 constexpr int MAX_SEG = 32;    // small frame subsets (PAM) are spread over more segments
-constexpr int EPI_HALVES = 2;  // two epilogue warps per TMEM lane quarter, NC/2 centres each
-constexpr int GROUPS_PER_HALF = NC / 8 / EPI_HALVES;  // groups of 8 centres per epilogue warp
-static_assert(NC % (8 * EPI_HALVES) == 0, "centre tile must split into groups of 8 per half");
-static_assert(3 * BN <= TMEM_COLS, "three accumulators must fit TMEM");
-static_assert(BN % 16 == 0 && BN <= 256, "UMMA N constraint for M = 128");
+static_assert(NC == 8 * EPI_PARTS * GROUPS_PER_WARP, "groups of 8 centres per epilogue warp");
+static_assert(ACC_SETS * ACC_COLS <= TMEM_COLS, "two accumulator sets must fit TMEM");
+static_assert(BN % 16 == 0 && BN <= 256 && BN >= BN_USED, "UMMA N constraint for M = 128");
+static_assert(B_TILE % 512 == 0 && STAGE_BYTES % 1024 == 0, "SWIZZLE_64B atoms stay aligned");
 
 // ---- operand split + packing -----------------------------------------------------------------
 // Writes, for every (tile T, k-block kb, sub-row-set s, h1|h2), the exact shared-memory image of
@@ -68,7 +82,9 @@ static_assert(BN % 16 == 0 && BN <= 256, "UMMA N constraint for M = 128");
 // stage arrives with ONE bulk copy instead of hundreds of 64-byte TMA row requests.
 //   image index = (((T * KB + kb) * S + s) * 2 + hl) * (RT * 64 bytes)
 //   source row  = (T * RT + r) * S + s   of the (rows_total x A_pad) float matrix `x`
-// Frames: RT = 128, S = 3 (the three coordinate rows of a frame); centres: RT = 144, S = 1.
+// Frames: RT = RU = 128, S = 3 (the three coordinate rows of a frame); centres: S = 1, RT = BN
+// image rows per tile of which the first RU = BN_USED carry source rows (T*RU + r), the rest
+// zeros (BN == BN_USED = 144 today).
 // `row_idx` (optional, frames only): tile row (T*RT + r) is frame row_idx[T*RT + r] of `x`.
 // One thread = one 16-byte chunk = 8 atoms.  *overflow is set when a coordinate cannot be
 // represented (|x| * 2^8 beyond the FP16 range): the caller then uses the exact kernel.
@@ -81,9 +97,9 @@ __device__ __forceinline__ void split_f16x2(float x, __half &h1, __half &h2, boo
 }
 
 __global__ void __launch_bounds__(256)
-k_pack_f16x2(const float *__restrict__ x, long rows_total, int A_pad, int RT, int S, long n_tiles,
-             const int64_t *__restrict__ row_idx, unsigned char *__restrict__ img, int *overflow,
-             const int *__restrict__ n_items_dev)
+k_pack_f16x2(const float *__restrict__ x, long rows_total, int A_pad, int RT, int RU, int S,
+             long n_tiles, const int64_t *__restrict__ row_idx, unsigned char *__restrict__ img,
+             int *overflow, const int *__restrict__ n_items_dev)
 {
     // optional device-side item count (PAM: the number of ambiguous frames is only known on
     // the device): rows of items beyond it are zero-filled and their row_idx is never read
@@ -97,13 +113,15 @@ k_pack_f16x2(const float *__restrict__ x, long rows_total, int A_pad, int RT, in
     for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (long)gridDim.x * blockDim.x) {
         const int q = (int)(t % Q);
-        const long rr = t / Q;           // (T, r, s) flattened as ((T*RT + r)*S + s)
-        const int sidx = (int)(rr % S);
-        const long tr = rr / S;          // T*RT + r
-        const long T = tr / RT;
-        const int r = (int)(tr - T * RT);
+        const long ri = t / Q;           // image row (T, r, s) flattened as ((T*RT + r)*S + s)
+        const int sidx = (int)(ri % S);
+        const long tri = ri / S;         // T*RT + r
+        const long T = tri / RT;
+        const int r = (int)(tri - T * RT);
+        const long tr = T * RU + r;      // source item (frame / centre row) of this image row
+        const long rr = tr * S + sidx;   // source row
         float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-        if (rr < rows_total && q < Qs) {
+        if (r < RU && rr < rows_total && q < Qs) {
             const long src = row_idx ? (long)__ldg(row_idx + tr) * S + sidx : rr;
             const float4 *p = reinterpret_cast<const float4 *>(x + (size_t)src * A_pad) + 2 * q;
             v0 = __ldg(p);
@@ -222,8 +240,8 @@ constexpr double kQcpSlack = 6.4e-5;
 struct Smem {
     uint64_t full[STAGES];
     uint64_t empty[STAGES];
-    uint64_t tmem_full;
-    uint64_t tmem_empty;
+    uint64_t tmem_full[ACC_SETS];
+    uint64_t tmem_empty[ACC_SETS];
     uint32_t tmem_base;
 };
 
@@ -256,8 +274,10 @@ k_tc_screen(const unsigned char *__restrict__ a_img, const unsigned char *__rest
             mbar_init(&sm->full[s], 1);
             mbar_init(&sm->empty[s], 1);
         }
-        mbar_init(&sm->tmem_full, 1);
-        mbar_init(&sm->tmem_empty, 4 * EPI_HALVES);
+        for (int a = 0; a < ACC_SETS; ++a) {
+            mbar_init(&sm->tmem_full[a], 1);
+            mbar_init(&sm->tmem_empty[a], EPI_WARPS);
+        }
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -302,15 +322,19 @@ k_tc_screen(const unsigned char *__restrict__ a_img, const unsigned char *__rest
         // ===================== MMA issuer =====================================================
         if (lane == 0) {
             int stage = 0;
-            uint32_t phase = 0, tphase = 0;
+            uint32_t phase = 0;
+            uint32_t tile_no = 0;          // centre tiles issued by this CTA: set = tile_no & 1
             for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const long ft = item / n_seg;
                 const int seg = (int)(item - ft * n_seg);
                 const int ct_hi = min(n_ct, (seg + 1) * ct_per_seg);
                 (void)ft;
-                for (int ct = seg * ct_per_seg; ct < ct_hi; ++ct) {
-                    mbar_wait(&sm->tmem_empty, tphase ^ 1);  // epilogue drained the accumulators
+                for (int ct = seg * ct_per_seg; ct < ct_hi; ++ct, ++tile_no) {
+                    const uint32_t as = tile_no % ACC_SETS;
+                    // the epilogue drained this accumulator set (its previous use)
+                    mbar_wait(&sm->tmem_empty[as], ((tile_no / ACC_SETS) & 1u) ^ 1u);
                     tc_fence_after();
+                    const uint32_t acc = tmem_base + as * (uint32_t)ACC_COLS;
                     for (int kb = 0; kb < KB; ++kb) {
                         mbar_wait(&sm->full[stage], phase);
                         tc_fence_after();
@@ -324,7 +348,7 @@ k_tc_screen(const unsigned char *__restrict__ a_img, const unsigned char *__rest
                             for (int i = 0; i < 3; ++i) {
                                 const uint64_t ahi = smem_desc_sw64(st + (2 * i) * A_TILE);
                                 const uint64_t alo = smem_desc_sw64(st + (2 * i + 1) * A_TILE);
-                                const uint32_t d = tmem_base + (uint32_t)(i * BN);
+                                const uint32_t d = acc + (uint32_t)(i * BN);
                                 const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
                                 tc_mma_f16(d, ahi + koff, bhi + koff, kIdesc, first);
                                 tc_mma_f16(d, ahi + koff, blo + koff, kIdesc, 1u);
@@ -337,19 +361,19 @@ k_tc_screen(const unsigned char *__restrict__ a_img, const unsigned char *__rest
                             phase ^= 1;
                         }
                     }
-                    tc_commit(&sm->tmem_full);
-                    tphase ^= 1;
+                    tc_commit(&sm->tmem_full[as]);
                 }
             }
         }
     } else {
         // ===================== epilogue: TMEM -> registers -> QCP ============================
-        // warp w (2..9): TMEM lane quarter w & 3 (hardware rule), centre half (w - 2) >> 2
+        // warp w (2..13): TMEM lane quarter w & 3 (hardware rule), centres 8*part .. 8*part+7 of
+        // the tile with part = (w - 2) >> 2
         const int q = warp & 3;
-        const int hh = (warp - 2) >> 2;            // which 16 of the tile's 32 centres
+        const int part = (warp - 2) >> 2;
         const int row = q * 32 + lane;             // frame within the tile
-        const int n_lists = n_seg * EPI_HALVES;
-        uint32_t tphase = 0;
+        const int n_lists = n_seg * EPI_PARTS;
+        uint32_t tile_no = 0;
         for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
             const long ft = item / n_seg;
             const int seg = (int)(item - ft * n_seg);
@@ -362,16 +386,17 @@ k_tc_screen(const unsigned char *__restrict__ a_img, const unsigned char *__rest
             // bounds are kept in units of N * msd
             double umin = 1e300;
             int ncand = 0;
-            const int lid = seg * EPI_HALVES + hh;
+            const int lid = seg * EPI_PARTS + part;
             const size_t slot = ((size_t)(fvalid ? f : 0) * n_lists + lid) * MAX_CAND;
-            for (int ct = seg * ct_per_seg; ct < ct_hi; ++ct) {
-                mbar_wait(&sm->tmem_full, tphase);
-                tphase ^= 1;
+            for (int ct = seg * ct_per_seg; ct < ct_hi; ++ct, ++tile_no) {
+                const uint32_t as = tile_no % ACC_SETS;
+                mbar_wait(&sm->tmem_full[as], (tile_no / ACC_SETS) & 1u);
                 tc_fence_after();
-                const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+                const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) +
+                                           as * (uint32_t)ACC_COLS;
 #pragma unroll 1
-                for (int gg = 0; gg < GROUPS_PER_HALF; ++gg) {   // 8 centres = 24 columns
-                    const int g = hh * GROUPS_PER_HALF + gg;
+                for (int gg = 0; gg < GROUPS_PER_WARP; ++gg) {   // 8 centres = 24 columns
+                    const int g = part * GROUPS_PER_WARP + gg;
                     float m[3][24];
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
@@ -381,6 +406,13 @@ k_tc_screen(const unsigned char *__restrict__ a_img, const unsigned char *__rest
                         tc_ld8(lane_addr + col + 16, &m[i][16]);
                     }
                     tc_wait_ld();
+                    if (gg == GROUPS_PER_WARP - 1) {
+                        // the warp's last accumulator values are in registers: hand TMEM back
+                        // BEFORE this group's QCP arithmetic, the next tile's MMAs run under it
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&sm->tmem_empty[as]);
+                    }
                     if (MODE == 2) {
                         // timing probe (mode 2): consume the accumulators without the QCP
                         float acc = 0.f;
@@ -471,9 +503,6 @@ k_tc_screen(const unsigned char *__restrict__ a_img, const unsigned char *__rest
                         }
                     }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm->tmem_empty);
             }
             if (MODE == 1 && fvalid) {
                 cand_umin[(size_t)f * n_lists + lid] = __double2float_ru(fmin(umin, 3.0e38));
@@ -690,15 +719,23 @@ static size_t tc_img_row_bytes(int n_atoms)
     return 2 * sizeof(__half) * 3 * (size_t)A_img;
 }
 
+// bytes of the packed centre image: per centre tile and k-block {h1, h2} x (BN rows x 64 B)
+static size_t tc_b_img_bytes(int n_atoms, int32_t k)
+{
+    const int KB = (rmsd_apad(n_atoms) + tc::BK - 1) / tc::BK;
+    const size_t n_ct = (size_t)((k + tc::NC - 1) / tc::NC) + 1;
+    return n_ct * KB * 2 * (size_t)tc::B_TILE;
+}
+
 size_t eb_tc_scratch_bytes(int64_t n, int n_atoms, int32_t k)
 {
     const size_t row = tc_img_row_bytes(n_atoms);
     const long n_ft = (n + tc::BM - 1) / tc::BM;
     const int n_ct = (k + tc::NC - 1) / tc::NC;
     const size_t n_lists = (size_t)tc_pick_nseg(n_ft < 1 ? 1 : n_ft, n_ct < 1 ? 1 : n_ct) *
-                           tc::EPI_HALVES;
+                           tc::EPI_PARTS;
     // split copies of frames and centres + candidate lists + flags
-    return row * (size_t)(n + tc::BM) + row * (size_t)(k + tc::NC) +
+    return row * (size_t)(n + tc::BM) + tc_b_img_bytes(n_atoms, k) +
            (size_t)n * n_lists *
                (sizeof(int) + sizeof(float) +
                 tc_max_cand((int)n_lists) * (sizeof(int) + sizeof(float))) +
@@ -745,14 +782,13 @@ int eb_rmsd_assign_tc_dev(const float *xyz_soa, const double *traces, int64_t n,
     const size_t row = tc_img_row_bytes(n_atoms);  // image bytes per frame / per centre
     // packed operand images (tile-padded): frames then centres
     const size_t a_rows = (size_t)((n + tc::BM - 1) / tc::BM) * tc::BM;   // frames, padded
-    const size_t c_rows = (size_t)((k + tc::NC - 1) / tc::NC) * tc::NC;   // centres, padded
     unsigned char *a_img = (unsigned char *)scratch;
     unsigned char *b_img = a_img + row * a_rows;
-    unsigned char *lists = b_img + row * c_rows;
+    unsigned char *lists = b_img + tc_b_img_bytes(n_atoms, k);
     const int n_ct_total = (k + tc::NC - 1) / tc::NC;
     const long n_ft = (n + tc::BM - 1) / tc::BM;
     const int n_seg = tc_pick_nseg(n_ft, n_ct_total);
-    const size_t n_lists = (size_t)n_seg * tc::EPI_HALVES;
+    const size_t n_lists = (size_t)n_seg * tc::EPI_PARTS;
     int *cand_list = (int *)lists;
     const int max_cand = tc_max_cand((int)n_lists);
     float *cand_bound = (float *)(cand_list + (size_t)n * n_lists * max_cand);
@@ -766,15 +802,17 @@ int eb_rmsd_assign_tc_dev(const float *xyz_soa, const double *traces, int64_t n,
         long total = n_ft * tc::BM * 3 * (long)(A_img / 8);
         long blocks = (total + 255) / 256;
         if (blocks > 32L * sm_count()) blocks = 32L * sm_count();
-        tc::k_pack_f16x2<<<(int)blocks, 256, 0, s>>>(xyz_soa, 3L * n, A_pad, tc::BM, 3, n_ft,
-                                                     frame_idx, a_img, f16_overflow, n_dev);
+        tc::k_pack_f16x2<<<(int)blocks, 256, 0, s>>>(xyz_soa, 3L * n, A_pad, tc::BM, tc::BM, 3,
+                                                     n_ft, frame_idx, a_img, f16_overflow,
+                                                     n_dev);
         EB_LAUNCH_CHECK();
         const long b_tiles = n_ct_total;
         total = b_tiles * tc::BN * (long)(A_img / 8);
         blocks = (total + 255) / 256;
         if (blocks > 32L * sm_count()) blocks = 32L * sm_count();
-        tc::k_pack_f16x2<<<(int)blocks, 256, 0, s>>>(centers_soa, 3L * k, A_pad, tc::BN, 1,
-                                                     b_tiles, nullptr, b_img, f16_overflow, nullptr);
+        tc::k_pack_f16x2<<<(int)blocks, 256, 0, s>>>(centers_soa, 3L * k, A_pad, tc::BN,
+                                                     tc::BN_USED, 1, b_tiles, nullptr, b_img,
+                                                     f16_overflow, nullptr);
         EB_LAUNCH_CHECK();
     }
     const size_t smem = (size_t)tc::STAGES * tc::STAGE_BYTES + sizeof(tc::Smem) + 1024;
