@@ -8,7 +8,8 @@ import os
 from .exception import DataInvalid
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libenspara_b200.so")
+#: ENSPARA_B200_LIB points at another build of the same library (developer A/B runs only)
+LIB_PATH = os.environ.get("ENSPARA_B200_LIB") or os.path.join(_HERE, "libenspara_b200.so")
 
 EB_OK, EB_ERR_INVALID, EB_ERR_CUDA, EB_ERR_LIMIT = 0, 1, 2, 3
 DT_F32, DT_F64, DT_I8, DT_I16, DT_I32, DT_I64 = range(6)

@@ -193,6 +193,10 @@ constexpr uint32_t kIdesc = (1u << 4)          // D format F32
 // so that |M'| <= 1 and the start g = (Ga+Gb)/(2s) >= 1 whatever the size of the molecule;
 // lam' = lambda_max / s.  Eight Newton steps from above, no early exit; `dl` returns the size
 // of the last step so that the caller can refuse to trust a solve that has not settled.
+#ifndef EB_TC_NEWTON
+#define EB_TC_NEWTON 8
+#endif
+constexpr int kNewtonSteps = EB_TC_NEWTON;
 __device__ __forceinline__ void qcp4_f32(const float M[4][9], const float g[4], float lam[4],
                                          float dl[4])
 {
@@ -221,7 +225,7 @@ __device__ __forceinline__ void qcp4_f32(const float M[4][9], const float g[4], 
         dl[p] = 0.f;
     }
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
+    for (int it = 0; it < kNewtonSteps; ++it) {
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
             const float l = lam[p], l2 = l * l;
