@@ -372,6 +372,216 @@ k_kcenters_step_rmsd(const float *__restrict__ xyz, const double *__restrict__ t
 }
 
 // ------------------------------------------------------------------------------------------
+// K1, persistent multi-iteration variant (single shard, shards that do not take the TMA
+// kernel): up to n_steps iterations of kcenters.py:217-226 in ONE cooperative launch.  On a
+// small trajectory the data is L2-resident and an iteration is a few microseconds of work under
+// ~20-30 us of per-launch cost (launch gap, prologue round trips, the single-CTA arg-max tail:
+// 39.5 us per iteration at config 1, 20 000 frames x 264 atoms = 63 MB).  Here the grid stays
+// resident: the shard arg-max is a grid barrier after which EVERY block reduces the per-block
+// partials itself and stages the winner's frame straight from xyz.  Same arithmetic, summation
+// order, tie rules and state protocol as k_kcenters_step_rmsd<true, kModeStep, 0, ROUNDS>, so
+// results are bit-identical and single launches and multi launches mix freely.
+// gbar: monotonically increasing arrival counter (a multiple of gridDim.x between launches).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int ROUNDS>
+__global__ void __launch_bounds__(kStepThreads, 2)
+k_kcenters_multi_rmsd(const float *__restrict__ xyz, const double *__restrict__ traces, long n,
+                      int A, int A_pad, long frame_offset, unsigned char *cand, float *dist,
+                      int *assign, int n_clusters_limit, double cutoff, eb_kc_state *state,
+                      int64_t *center_list, Partial *partials, unsigned long long *gbar,
+                      int n_steps)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    StepSmem *ss = reinterpret_cast<StepSmem *>(smem_raw);
+    double *sums = reinterpret_cast<double *>(smem_raw + align16(sizeof(StepSmem)));
+    double *center_base = sums + kStepWarps * 32 * kSumStride;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 3, l8 = lane & 7;
+    const int A4 = A_pad >> 2;
+    const unsigned G = gridDim.x;
+    CenterSmem cs = center_smem_carve(center_base, A4);
+
+    // nobody writes *state / the counter's base before the first barrier: these reads agree
+    const int k0 = *reinterpret_cast<const volatile int32_t *>(&state->n_centers);
+    const int done0 = *reinterpret_cast<const volatile int32_t *>(&state->done);
+    const unsigned long long gbase = (ld_acquire_gpu(gbar) / G) * G;
+
+    constexpr int FPC = 4 * ROUNDS;
+    const long n_chunks = (n + FPC - 1) / FPC;
+    const long warps_total = (long)G * kStepWarps;
+    double *my_sums = sums + (size_t)warp * 32 * kSumStride;
+
+    int it = 0;
+    bool stopped = false;
+    double win_d = 0.0;
+    int64_t win_i = -1;
+    for (; it < n_steps; ++it) {
+        // ---- the centre of this iteration: candidate record (first) or the partials ---------
+        const float *src;
+        double Gb;
+        bool have;
+        if (it == 0) {
+            const RecHeader *h = reinterpret_cast<const RecHeader *>(cand);
+            win_d = __ldcg(&h->dist);
+            win_i = __ldcg(reinterpret_cast<const long long *>(&h->index));
+            Gb = __ldcg(&h->trace);
+            have = win_i >= 0;
+            src = reinterpret_cast<const float *>(cand + sizeof(RecHeader));
+        } else {
+            const Partial *pp = partials + (size_t)((it - 1) & 1) * G;
+            double d = -2.0;
+            int64_t i = INT64_MAX;
+            for (unsigned b = threadIdx.x; b < G; b += blockDim.x) {
+                const double od = __ldcg(&pp[b].dist);
+                const int64_t oi = __ldcg(reinterpret_cast<const long long *>(&pp[b].index));
+                if (better(od, oi, d, i)) {
+                    d = od;
+                    i = oi;
+                }
+            }
+            block_argmax(d, i, ss->red);
+            if (threadIdx.x == 0) {
+                ss->red[0].dist = d;
+                ss->red[0].index = i;
+            }
+            __syncthreads();
+            d = ss->red[0].dist;
+            i = ss->red[0].index;
+            __syncthreads();
+            have = i != INT64_MAX;
+            win_d = have ? d : -1.0;
+            win_i = have ? frame_offset + i : -1;
+            src = xyz + (size_t)(have ? i : 0) * 3 * A_pad;
+            Gb = have ? traces[i] : 0.0;
+        }
+        const int k = k0 + it;
+        if (!(have && !done0 && k < n_clusters_limit && win_d > cutoff)) {   // kcenters.py:217
+            stopped = true;
+            break;
+        }
+        center_smem_fill(cs, src, A_pad);
+        if (blockIdx.x == 0 && threadIdx.x == 0) center_list[k] = win_i;
+        __syncthreads();
+
+        // ---- body: identical to k_kcenters_step_rmsd<true, kModeStep, 0, ROUNDS> -------------
+        double best_d = -2.0;
+        int64_t best_i = INT64_MAX;
+        for (long chunk = (long)blockIdx.x * kStepWarps + warp; chunk < n_chunks;
+             chunk += warps_total) {
+            const long base = chunk * FPC;
+            const long f = (lane < FPC) ? base + lane : n;
+#pragma unroll 1
+            for (int s = 0; s < ROUNDS; ++s) {
+                const long fs = base + 4 * s + g;
+                double m[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                if (fs < n)
+                    frame_inner_products<true, 0>(m, xyz + (size_t)fs * 3 * A_pad, A4, l8, cs);
+                group8_reduce(m);
+                if (l8 == 0) {
+                    double *dst = my_sums + (4 * s + g) * kSumStride;
+#pragma unroll
+                    for (int e = 0; e < 9; ++e) dst[e] = m[e];
+                }
+            }
+            __syncwarp();
+            if (f < n) {
+                double m[9];
+                const double *srcm = my_sums + lane * kSumStride;
+#pragma unroll
+                for (int e = 0; e < 9; ++e) m[e] = srcm[e];
+                const float d = rmsd_from_msd(qcp_msd(m, traces[f], Gb, A));
+                const float old = dist[f];
+                if (d < old) {  // strict '<', kcenters.py:304
+                    dist[f] = d;
+                    assign[f] = k;
+                }
+                const double cur = (double)((d < old) ? d : old);
+                if (cur > best_d) {  // frames arrive in increasing f per lane: first max kept
+                    best_d = cur;
+                    best_i = f;
+                }
+            }
+            __syncwarp();
+        }
+        // ---- shard arg-max: per-block partial, grid barrier ------------------------------------
+        block_argmax(best_d, best_i, ss->red);
+        if (threadIdx.x == 0) {
+            Partial *pp = partials + (size_t)(it & 1) * G;
+            pp[blockIdx.x].dist = best_d;
+            pp[blockIdx.x].index = best_i;
+            __threadfence();
+            atomicAdd(gbar, 1ull);
+            const unsigned long long target = gbase + (unsigned long long)(it + 1) * G;
+            while (ld_acquire_gpu(gbar) < target) __nanosleep(32);
+        }
+        __syncthreads();
+    }
+    if (blockIdx.x != 0) return;
+
+    // ---- block 0: leave *state and the candidate record as a chain of single steps would ----
+    if (it > 0) {
+        const Partial *pp = partials + (size_t)((it - 1) & 1) * G;
+        double d = -2.0;
+        int64_t i = INT64_MAX;
+        for (unsigned b = threadIdx.x; b < G; b += blockDim.x) {
+            const double od = __ldcg(&pp[b].dist);
+            const int64_t oi = __ldcg(reinterpret_cast<const long long *>(&pp[b].index));
+            if (better(od, oi, d, i)) {
+                d = od;
+                i = oi;
+            }
+        }
+        block_argmax(d, i, ss->red);
+        if (threadIdx.x == 0) {
+            ss->red[0].dist = d;
+            ss->red[0].index = i;
+        }
+        __syncthreads();
+        d = ss->red[0].dist;
+        i = ss->red[0].index;
+        const bool empty = (i == INT64_MAX);
+        RecHeader *out = reinterpret_cast<RecHeader *>(cand);
+        if (!empty) {
+            const float4 *srow = reinterpret_cast<const float4 *>(xyz + (size_t)i * 3 * A_pad);
+            float4 *dst = reinterpret_cast<float4 *>(cand + sizeof(RecHeader));
+            for (int t = threadIdx.x; t < 3 * A4; t += blockDim.x) dst[t] = __ldcg(srow + t);
+        }
+        if (threadIdx.x == 0) {
+            out->dist = empty ? -1.0 : d;
+            out->index = empty ? -1 : frame_offset + i;
+            out->trace = empty ? 0.0 : traces[i];
+            out->reserved = 0;
+            state->n_centers = k0 + it;
+            state->last_center = center_list[k0 + it - 1];
+            state->local_maxdist = empty ? -1.0 : d;
+        }
+    }
+    if (threadIdx.x == 0) {
+        if (stopped) {
+            if (!done0) {
+                state->done = 1;
+                state->maxdist = win_d;
+                state->n_noop += n_steps - it - 1;
+            } else {
+                state->n_noop += n_steps;
+            }
+        } else {
+            state->maxdist = win_d;
+        }
+        state->blocks_done = 0;
+        __threadfence();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // K1, TMA-staged variant of the step: same contract, same arithmetic and the SAME summation
 // order as k_kcenters_step_rmsd<true, kModeStep, 0, 8> (8 lanes per frame, lane l8 adds atoms
 // 4j..4j+3 for j = l8, l8+8, ... in increasing j, butterfly over the 8 lanes), so results are
@@ -748,6 +958,51 @@ static int launch_step_v(const float *xyz, const double *traces, long n, int A, 
 #undef EB_STEP_ARGS
 }
 
+// Persistent multi-iteration launch (single shard, exact arithmetic, non-TMA shapes).  *used = 0
+// when not eligible; the caller then queues single steps.
+template <int ROUNDS>
+static int launch_multi_r(const float *xyz, const double *traces, long n, int A, long frame_offset,
+                          void *cand, float *dist, int *assign, int limit, double cutoff,
+                          eb_kc_state *state, int64_t *center_list, void *partials, int n_steps,
+                          cudaStream_t stream, int *used)
+{
+    *used = 0;
+    int A_pad = rmsd_apad(A);
+    const size_t smem = step_smem_bytes(A_pad);
+    if (smem > 227 * 1024) return EB_OK;
+    static int coop = -1;
+    if (coop < 0) {
+        int dev = 0, v = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev);
+        coop = v;
+    }
+    if (!coop) return EB_OK;
+    auto kern = k_kcenters_multi_rmsd<ROUNDS>;
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+        configured = smem;
+    }
+    int per_sm = 0;
+    EB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kStepThreads, smem));
+    if (per_sm < 1) return EB_OK;
+    int grid = step_grid(n, 4 * ROUNDS);
+    const long cap = (long)per_sm * sm_count();
+    if (grid > cap) grid = (int)cap;
+    if (2 * grid > kMaxGrid) return EB_OK;
+    unsigned char *candp = (unsigned char *)cand;
+    Partial *pp = (Partial *)partials;
+    unsigned long long *gbar = reinterpret_cast<unsigned long long *>(&state->reserved);
+    void *args[] = {&xyz, &traces, &n, &A, &A_pad, &frame_offset, &candp, &dist, &assign, &limit,
+                    &cutoff, &state, &center_list, &pp, &gbar, &n_steps};
+    EB_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(kStepThreads), args,
+                                        smem, stream));
+    *used = 1;
+    return EB_OK;
+}
+
 template <bool EXACT, int MODE, typename... Args> static int launch_step(Args... args)
 {
     if (MODE == kModeSeed) return launch_step_v<EXACT, MODE, 0>(args...);
@@ -871,6 +1126,29 @@ static int step_rmsd_impl(const float *xyz_soa, const double *traces, int64_t n,
             EB_LAUNCH_CHECK();
         }
         return EB_OK;
+    }
+    // single shard, several iterations queued at once, not the TMA kernel: one persistent
+    // cooperative launch for the whole batch (EB_K1_MULTI=0 forces one launch per iteration)
+    static const int multi_on = [] {
+        const char *e = getenv("EB_K1_MULTI");
+        return e ? atoi(e) : 1;
+    }();
+    if (multi_on && n_steps > 1 && exact && k1_variant() == 0 && !exch.peers && n_cand == 1 &&
+        cand_in == cand_out && n > 0) {
+        int used = 0, rc = EB_OK;
+        switch (pick_rounds(n)) {
+#define EB_MULTI_ARGS                                                                             \
+    xyz_soa, traces, (long)n, n_atoms, (long)frame_offset, cand_out, dist, assign,                \
+        (int)n_clusters_limit, dist_cutoff, state, center_list, partials, n_steps,                \
+        (cudaStream_t)stream, &used
+            case 1: rc = launch_multi_r<1>(EB_MULTI_ARGS); break;
+            case 2: rc = launch_multi_r<2>(EB_MULTI_ARGS); break;
+            case 4: rc = launch_multi_r<4>(EB_MULTI_ARGS); break;
+            default: rc = launch_multi_r<8>(EB_MULTI_ARGS); break;
+#undef EB_MULTI_ARGS
+        }
+        if (rc != EB_OK) return rc;
+        if (used) return EB_OK;
     }
     StepExtra ex;
     ex.exch = exch;

@@ -283,3 +283,46 @@ def test_triangle_inequality_warm_start(cuda):
     # and a warm start continues exactly where the cold run would have gone
     cold = kcenters.kcenters(X, "rmsd", n_clusters=60)
     assert [int(c) for c in cold.center_indices][20:] == [int(c) for c in b.center_indices][20:]
+
+
+@pytest.mark.parametrize("n,A", [(20_000, 264), (3001, 50), (700, 22), (40_000, 500)])
+def test_persistent_multi_iteration_kernel_equals_single_launches(cuda, n, A):
+    """csrc/eb_rmsd_kcenters.cu k_kcenters_multi_rmsd: a batch of iterations on a single shard
+    that does not take the TMA kernel runs as ONE cooperative launch.  Driving the engine one
+    step at a time (the single-launch kernel) and in batches (the persistent kernel, also mixed
+    with single steps) must give identical centres, assignments and distances -- bit for bit,
+    the summation order is the same -- including a cutoff that fires inside a batch."""
+    torch = cuda
+    from enspara_b200 import _lib, synth
+    from enspara_b200.cluster import kcenters as kc
+    from enspara_b200.cluster._engine import KCentersEngine
+    assert not _lib.load().eb_kcenters_step_rmsd_uses_tma(n, A)
+    X = synth.device_trajectory(n, A, seed=A)
+
+    def drive(batches, limit=1 << 30, cutoff=0.0):
+        eng = KCentersEngine(X, "rmsd", kc._SingleComm())
+        eng._ensure_center_list(128)
+        eng.seed(0)
+        for b in batches:
+            eng.step(limit, cutoff, b)
+        st = eng.read_state()
+        k = int(st.n_centers)
+        return (k, int(st.done), eng.center_list[:k].cpu().numpy().tolist(), eng.assign.clone(),
+                eng.dist.clone(), float(st.maxdist))
+    single = drive([1] * 37)
+    multi = drive([37])
+    mixed = drive([1, 5, 1, 27, 3])
+    for other in (multi, mixed):
+        assert other[0] == single[0] == 37 and other[2] == single[2]
+        assert torch.equal(other[3], single[3]) and torch.equal(other[4], single[4])
+    # a cutoff between the 20th and 21st max-min-distance stops a 37-launch batch inside
+    d_sorted = drive([21])[5], drive([22])[5]
+    cut = 0.5 * (d_sorted[0] + d_sorted[1])
+    a = drive([1] * 37, cutoff=cut)
+    b = drive([37], cutoff=cut)
+    assert a[0] == b[0] and a[1] == b[1] == 1 and a[2] == b[2]
+    assert torch.equal(a[3], b[3]) and torch.equal(a[4], b[4])
+    # ... and an n_clusters limit inside a batch
+    c = drive([1] * 20, limit=11)
+    d = drive([20], limit=11)
+    assert c[0] == d[0] == 11 and c[2] == d[2] and torch.equal(c[4], d[4])
