@@ -48,13 +48,32 @@ struct RecHeader {
 };
 static_assert(sizeof(RecHeader) == 32, "record header is 32 bytes");
 
-// Padded atom count.  Rows are always 32-byte (sector) aligned; when rounding up to a multiple
-// of 32 atoms costs at most 3% extra bytes the rows become 128-byte (cache line) aligned, which
-// makes every 8-lane request exactly one line (otherwise L1 pulls both straddled lines from L2).
+// Row parts of the TMA-staged step kernel: a coordinate row of A_pad = 32 m floats is cut into
+// P parts of whole 128-byte lines, each at most 256 floats (the TMA box limit).  Returns the
+// smallest such P in 1..4, or 0 when there is none (m prime > 8, m > 32, ...).
+__host__ __device__ inline int rmsd_tma_parts(int A_pad)
+{
+    if (A_pad <= 0 || (A_pad & 31)) return 0;
+    const int m = A_pad >> 5;
+    for (int P = 1; P <= 4; ++P)
+        if (m % P == 0 && m / P <= 8) return P;
+    return 0;
+}
+
+// Padded atom count.  Rows are always 32-byte (sector) aligned.  Rows of whole 128-byte lines
+// (a multiple of 32 atoms) make every 8-lane request exactly one line (otherwise L1 pulls both
+// straddled lines from L2) AND let large shards take the TMA-staged step kernel, which needs
+// row parts of whole lines: worth up to 12 % of extra (zero) bytes -- measured at 264 atoms the
+// unaligned LDG kernel reaches 78 % of the copy peak, the aligned kernels 91 % (LDG) / 103 %
+// (TMA), so 264 -> 288 (+9 %) is a net gain.  The smallest multiple of 32 that the TMA kernel
+// can cut into parts is preferred; otherwise any multiple of 32 within 3 %; otherwise a
+// multiple of 8.  Padding atoms are zeros: they change no sum (results do not depend on A_pad).
 __host__ __device__ inline int rmsd_apad(int n_atoms)
 {
     const int a8 = (n_atoms + 7) & ~7;
     const int a32 = (n_atoms + 31) & ~31;
+    for (int a = a32; a * 100 <= n_atoms * 112; a += 32)
+        if (rmsd_tma_parts(a)) return a;
     return (a32 * 100 <= n_atoms * 103) ? a32 : a8;
 }
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }

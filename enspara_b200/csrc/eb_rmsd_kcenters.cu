@@ -830,7 +830,11 @@ static size_t step_tma_smem_bytes(int A_pad, int P, int S)
 }
 
 constexpr int kTmaRingStages = 2;
-static int tma_parts(int A_pad) { return A_pad <= 256 ? 1 : (A_pad <= 512 ? 2 : 4); }
+static int tma_parts(int A_pad)
+{
+    const int P = rmsd_tma_parts(A_pad);
+    return P ? P : 1;   // callers check rmsd_tma_parts() != 0 through step_uses_tma()
+}
 static int k1_tma_enabled();
 static int pick_rounds(long n);
 static int k1_variant();
@@ -843,7 +847,8 @@ static bool step_uses_tma(long n, int n_atoms)
     const int P = tma_parts(A_pad);
     return k1_tma_enabled() && k1_variant() == 0 &&
            step_tma_smem_bytes(A_pad, P, kTmaRingStages) <= 227 * 1024 && pick_rounds(n) == 8 &&
-           A_pad / P <= 256 && A_pad % (32 * P) == 0 && 3 * n < (int64_t(1) << 31);
+           rmsd_tma_parts(A_pad) != 0 && A_pad / P <= 256 && A_pad % (32 * P) == 0 &&
+           3 * n < (int64_t(1) << 31);
 }
 
 // TMA-staged kernel for large shards (default); EB_K1_TMA=0 forces the LDG kernel (A/B switch)
@@ -1110,6 +1115,7 @@ static int step_rmsd_impl(const float *xyz_soa, const double *traces, int64_t n,
         if (trc != EB_OK) return trc;
         auto kern = k_kcenters_step_rmsd_tma<2, S>;
         if (P == 1) kern = k_kcenters_step_rmsd_tma<1, S>;
+        if (P == 3) kern = k_kcenters_step_rmsd_tma<3, S>;
         if (P == 4) kern = k_kcenters_step_rmsd_tma<4, S>;
         EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)tma_smem));
@@ -1336,6 +1342,7 @@ int eb_rmsd_one_to_all(const float *xyz_soa, const double *traces, int64_t n, in
         if (trc != EB_OK) return trc;
         auto kern = k_kcenters_step_rmsd_tma<2, S, kModeDistOnly>;
         if (P == 1) kern = k_kcenters_step_rmsd_tma<1, S, kModeDistOnly>;
+        if (P == 3) kern = k_kcenters_step_rmsd_tma<3, S, kModeDistOnly>;
         if (P == 4) kern = k_kcenters_step_rmsd_tma<4, S, kModeDistOnly>;
         EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)tma_smem));

@@ -81,7 +81,21 @@ def c1():
     est2, dt2 = timed(lambda: KCenters("rmsd", n_clusters=100).fit(dev))
     same = [int(c) for c in est.result_.center_indices] == \
         [int(c) for c in est2.result_.center_indices]
+    # the device loop alone (CUDA events around the queued iterations)
+    from enspara_b200.cluster._engine import KCentersEngine
+    from enspara_b200.cluster.kcenters import _SingleComm
+    loop_us = None
+    for _ in range(2):
+        eng = KCentersEngine(dev, "rmsd", _SingleComm())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync()
+        e0.record()
+        eng.run(100, 0.0)
+        e1.record()
+        sync()
+        loop_us = 1e3 * e0.elapsed_time(e1) / 100
     return {"config": "C1 KCenters rmsd k=100, 20k x 264 (host ndarray in, results out)",
+            "device_loop_us_per_iteration": loop_us,
             "seconds_host_in": dt, "evals_per_s_host_in": 20_000 * 100 / dt,
             "seconds_resident": dt2, "evals_per_s_resident": 20_000 * 100 / dt2,
             "us_per_iteration_resident": 1e6 * dt2 / 100,

