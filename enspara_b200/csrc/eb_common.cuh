@@ -49,25 +49,27 @@ struct RecHeader {
 static_assert(sizeof(RecHeader) == 32, "record header is 32 bytes");
 
 // Row parts of the TMA-staged step kernel: a coordinate row of A_pad = 32 m floats is cut into
-// P parts of whole 128-byte lines, each at most 256 floats (the TMA box limit).  Returns the
-// smallest such P in 1..4, or 0 when there is none (m prime > 8, m > 32, ...).
+// P parts of whole 128-byte lines, each at most 256 floats (the TMA box limit) and at least 160
+// floats (640 bytes: smaller stages lose to the LDG kernel -- measured at 1.25M frames, rows of
+// 288 floats cut into 3 x 96: TMA 0.846 ms, LDG 0.806 ms; rows of 384 = 2 x 192: TMA 0.891 ms,
+// LDG 0.994 ms).  Returns the smallest such P in 1..4, or 0 when there is none.
 __host__ __device__ inline int rmsd_tma_parts(int A_pad)
 {
     if (A_pad <= 0 || (A_pad & 31)) return 0;
     const int m = A_pad >> 5;
     for (int P = 1; P <= 4; ++P)
-        if (m % P == 0 && m / P <= 8) return P;
+        if (m % P == 0 && m / P <= 8 && m / P >= 5) return P;
     return 0;
 }
 
-// Padded atom count.  Rows are always 32-byte (sector) aligned.  Rows of whole 128-byte lines
-// (a multiple of 32 atoms) make every 8-lane request exactly one line (otherwise L1 pulls both
-// straddled lines from L2) AND let large shards take the TMA-staged step kernel, which needs
-// row parts of whole lines: worth up to 12 % of extra (zero) bytes -- measured at 264 atoms the
-// unaligned LDG kernel reaches 78 % of the copy peak, the aligned kernels 91 % (LDG) / 103 %
-// (TMA), so 264 -> 288 (+9 %) is a net gain.  The smallest multiple of 32 that the TMA kernel
-// can cut into parts is preferred; otherwise any multiple of 32 within 3 %; otherwise a
-// multiple of 8.  Padding atoms are zeros: they change no sum (results do not depend on A_pad).
+// Padded atom count.  Rows are always 32-byte (sector) aligned.  When a multiple of 32 atoms
+// that the TMA-staged kernel can cut into parts is within 12 % it is taken (large shards then
+// stream at 88-103 % of the copy peak instead of the LDG kernel's 75-81 %: 350 -> 384 atoms
+// 80.9 % -> 90.2 % algorithmic, 240 -> 256 81.6 %); otherwise any multiple of 32 within 3 %
+// (whole 128-byte lines per 8-lane request); otherwise a multiple of 8 -- e.g. 264 atoms stay
+// 264: padded to 288 (3 x 96 floats) both kernels were slower than the unpadded LDG kernel
+// (75 % / 72 % vs 78 %).  Padding atoms are zeros: they change no sum, so results do not
+// depend on A_pad.
 __host__ __device__ inline int rmsd_apad(int n_atoms)
 {
     const int a8 = (n_atoms + 7) & ~7;

@@ -829,13 +829,47 @@ static size_t step_tma_smem_bytes(int A_pad, int P, int S)
            sizeof(double) * kStepWarps * 32 * kSumStride + sizeof(double) * 3 * (size_t)A_pad;
 }
 
-constexpr int kTmaRingStages = 2;
-static int tma_parts(int A_pad)
+// Ring configuration of the TMA-staged kernel for rows of A_pad floats: P parts per row (whole
+// 128-byte lines, <= 256 floats, P in 1..4) and S stages per warp.  Big copies win (measured at
+// 500 atoms: (P,S) = (2,2) 1.11 ms, (4,4) 1.22, (8,8) 1.56), so the smallest P whose 2-stage
+// ring fits shared memory is taken; when a stage is small (part rows under 1 KB) the ring is
+// deepened to 4 where shared memory allows.  Parts under 640 bytes are not worth it (see
+// rmsd_tma_parts in eb_common.cuh).  Returns false when the row cannot be cut.
+static bool tma_config(int A_pad, int *P_out, int *S_out)
 {
-    const int P = rmsd_tma_parts(A_pad);
-    return P ? P : 1;   // callers check rmsd_tma_parts() != 0 through step_uses_tma()
+    if (A_pad <= 0 || (A_pad & 31)) return false;
+    const int m = A_pad >> 5;
+    for (int P = 1; P <= 4; ++P) {
+        if (m % P != 0 || m / P > 8 || m / P < 5) continue;   // parts of 160..256 floats
+        if (step_tma_smem_bytes(A_pad, P, 2) > 227 * 1024) continue;
+        int S = 2;
+        const size_t part_row_bytes = 4 * (size_t)A_pad / P;
+        if (part_row_bytes < 1024 && step_tma_smem_bytes(A_pad, P, 4) <= 227 * 1024) S = 4;
+        *P_out = P;
+        *S_out = S;
+        return true;
+    }
+    return false;
 }
 static int k1_tma_enabled();
+template <int MODE>
+static auto tma_kernel(int P, int S) -> decltype(&k_kcenters_step_rmsd_tma<1, 2, MODE>)
+{
+    if (S == 4) {
+        switch (P) {
+            case 1: return k_kcenters_step_rmsd_tma<1, 4, MODE>;
+            case 2: return k_kcenters_step_rmsd_tma<2, 4, MODE>;
+            case 3: return k_kcenters_step_rmsd_tma<3, 4, MODE>;
+            default: return k_kcenters_step_rmsd_tma<4, 4, MODE>;
+        }
+    }
+    switch (P) {
+        case 1: return k_kcenters_step_rmsd_tma<1, 2, MODE>;
+        case 2: return k_kcenters_step_rmsd_tma<2, 2, MODE>;
+        case 3: return k_kcenters_step_rmsd_tma<3, 2, MODE>;
+        default: return k_kcenters_step_rmsd_tma<4, 2, MODE>;
+    }
+}
 static int pick_rounds(long n);
 static int k1_variant();
 
@@ -844,11 +878,9 @@ static int k1_variant();
 static bool step_uses_tma(long n, int n_atoms)
 {
     const int A_pad = rmsd_apad(n_atoms);
-    const int P = tma_parts(A_pad);
-    return k1_tma_enabled() && k1_variant() == 0 &&
-           step_tma_smem_bytes(A_pad, P, kTmaRingStages) <= 227 * 1024 && pick_rounds(n) == 8 &&
-           rmsd_tma_parts(A_pad) != 0 && A_pad / P <= 256 && A_pad % (32 * P) == 0 &&
-           3 * n < (int64_t(1) << 31);
+    int P = 0, S = 0;
+    return k1_tma_enabled() && k1_variant() == 0 && tma_config(A_pad, &P, &S) &&
+           pick_rounds(n) == 8 && 3 * n < (int64_t(1) << 31);
 }
 
 // TMA-staged kernel for large shards (default); EB_K1_TMA=0 forces the LDG kernel (A/B switch)
@@ -1102,10 +1134,9 @@ static int step_rmsd_impl(const float *xyz_soa, const double *traces, int64_t n,
     // ring (P,S) = (2,2) 1.11; (4,4) 1.22; (8,8) 1.56 -- big copies win, so P is the smallest
     // split that respects the 256-element box limit and S = 2 fills shared memory.
     const int A_pad_ = rmsd_apad(n_atoms);
-    constexpr int S = kTmaRingStages;
-    const int P = tma_parts(A_pad_);
+    int P = 1, S = 2;
+    const bool use_tma = exact && step_uses_tma(n, n_atoms) && tma_config(A_pad_, &P, &S);
     const size_t tma_smem = step_tma_smem_bytes(A_pad_, P, S);
-    const bool use_tma = exact && step_uses_tma(n, n_atoms);
     if (use_tma) {
         CUtensorMap tmap;
         const int trc = make_tmap_2d(&tmap, xyz_soa, CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
@@ -1113,10 +1144,7 @@ static int step_rmsd_impl(const float *xyz_soa, const double *traces, int64_t n,
                                      (uint64_t)A_pad_ * sizeof(float), 12,
                                      (uint32_t)(A_pad_ / P), CU_TENSOR_MAP_SWIZZLE_NONE);
         if (trc != EB_OK) return trc;
-        auto kern = k_kcenters_step_rmsd_tma<2, S>;
-        if (P == 1) kern = k_kcenters_step_rmsd_tma<1, S>;
-        if (P == 3) kern = k_kcenters_step_rmsd_tma<3, S>;
-        if (P == 4) kern = k_kcenters_step_rmsd_tma<4, S>;
+        auto kern = tma_kernel<kModeStep>(P, S);
         EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)tma_smem));
         const size_t rec_bytes = sizeof(RecHeader) + sizeof(float) * 3 * (size_t)A_pad_;
@@ -1331,8 +1359,8 @@ int eb_rmsd_one_to_all(const float *xyz_soa, const double *traces, int64_t n, in
                  "rmsd_one_to_all: null pointer");
     if (exact && step_uses_tma(n, n_atoms)) {
         const int A_pad = rmsd_apad(n_atoms);
-        constexpr int S = kTmaRingStages;
-        const int P = tma_parts(A_pad);
+        int P = 1, S = 2;
+        tma_config(A_pad, &P, &S);
         const size_t tma_smem = step_tma_smem_bytes(A_pad, P, S);
         CUtensorMap tmap;
         const int trc = make_tmap_2d(&tmap, xyz_soa, CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
@@ -1340,10 +1368,7 @@ int eb_rmsd_one_to_all(const float *xyz_soa, const double *traces, int64_t n, in
                                      (uint64_t)A_pad * sizeof(float), 12, (uint32_t)(A_pad / P),
                                      CU_TENSOR_MAP_SWIZZLE_NONE);
         if (trc != EB_OK) return trc;
-        auto kern = k_kcenters_step_rmsd_tma<2, S, kModeDistOnly>;
-        if (P == 1) kern = k_kcenters_step_rmsd_tma<1, S, kModeDistOnly>;
-        if (P == 3) kern = k_kcenters_step_rmsd_tma<3, S, kModeDistOnly>;
-        if (P == 4) kern = k_kcenters_step_rmsd_tma<4, S, kModeDistOnly>;
+        auto kern = tma_kernel<kModeDistOnly>(P, S);
         EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)tma_smem));
         long blocks = ((n + 31) / 32 + kStepWarps - 1) / kStepWarps;

@@ -328,12 +328,13 @@ def test_persistent_multi_iteration_kernel_equals_single_launches(cuda, n, A):
     assert c[0] == d[0] == 11 and c[2] == d[2] and torch.equal(c[4], d[4])
 
 
-@pytest.mark.parametrize("A", [264, 240, 700])
+@pytest.mark.parametrize("A", [350, 240, 700, 600])
 def test_tma_step_kernel_for_rows_that_are_not_whole_lines(cuda, A):
-    """Atom counts whose rows are not whole 128-byte lines (config 1's 264 atoms: rows padded
-    288 = 3 parts of 96 floats; 240 -> 256, one part; 700 -> 768, three parts of 256): large
-    shards take the TMA-staged step kernel.  80 000 frames through the estimator; a sample of
-    frames against the oracle's brute-force nearest centre."""
+    """Atom counts whose rows are not whole 128-byte lines are padded to a multiple of 32 atoms
+    when the TMA-staged step kernel can cut the row into parts of 160..256 floats (350 -> 384 =
+    2 x 192; 240 -> 256, one part; 700 -> 768 = 4 x 192; 600 -> 640 = 4 x 160), so large shards
+    take that kernel.  80 000 frames through the estimator; a sample of frames against the
+    oracle's brute-force nearest centre."""
     from enspara_b200 import _lib, synth
     from enspara_b200.cluster import KCenters
     from oracle import cluster as oc
