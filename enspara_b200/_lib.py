@@ -82,6 +82,8 @@ SIGNATURES = {
     "eb_sum_squares": (_int, [_vp, _i64, _int, _vp, _vp, _vp]),
     "eb_count_members": (_int, [_vp, _i64, _i32, _vp, _vp]),
     "eb_select_member": (_int, [_vp, _i64, _i32, _i64, _vp, _vp, _vp]),
+    "eb_xtc_scan": (_int, [ctypes.c_char_p, _vp, _vp]),
+    "eb_xtc_read": (_int, [ctypes.c_char_p, _i64, _i64, _i64, _vp, _i32, _vp, _vp]),
     "eb_synth_trajectory_aos": (_int, [_vp, _i64, _int, _i64, _u64, _vp, _int, _vp]),
     "eb_synth_features": (_int, [_vp, _i64, _i64, _i64, _u64, _vp]),
 }

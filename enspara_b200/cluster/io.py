@@ -86,17 +86,27 @@ def load_features(features, stride):
     return lengths, data
 
 
-def load_trajectories(topologies, trajectories, selections, stride):
-    """Trajectory files -> (global lengths, md.Trajectory of this rank's frames); file i of the
-    flattened list goes to rank i % size (util.py:350-404, mpi/io.py:142-194).  Needs mdtraj."""
+def _traj_backend():
+    """mdtraj when it is installed, else the native readers of util/traj.py (.xtc + .pdb)."""
     try:
         import mdtraj as md
+        if getattr(md, "__file__", None) and hasattr(md, "load"):
+            return md, True
     except ImportError:
-        raise ImproperlyConfigured(
-            "Loading trajectory files needs mdtraj, which is not installed.")
+        pass
+    from ..util import traj
+    return traj, False
+
+
+def load_trajectories(topologies, trajectories, selections, stride):
+    """Trajectory files -> (global lengths, Trajectory of this rank's frames); file i of the
+    flattened list goes to rank i % size (util.py:350-404, mpi/io.py:142-194).  With mdtraj
+    every format it reads; without it .xtc trajectories with .pdb topologies (native decoder,
+    stride and atom selection applied while decoding)."""
+    md, have_md = _traj_backend()
     flat, tops, inds, n_inds, top = [], [], [], None, None
     for topfile, trjset, selection in zip(topologies, trajectories, selections):
-        top = md.load(topfile).top
+        top = md.load(topfile).top if have_md else md.load_topology(topfile)
         try:
             indices = top.select(selection)
         except Exception:
@@ -112,6 +122,8 @@ def load_trajectories(topologies, trajectories, selections, stride):
             flat.append(trj)
             tops.append(top)
             inds.append(indices)
+    if n_inds == 0:
+        raise ImproperlyConfigured("No atoms selected for clustering")   # util.py:386 (assert)
     if len(flat) < mpi.size():
         raise ImproperlyConfigured(
             "To stripe files across workers, at least 1 file per rank must be given.")
@@ -147,16 +159,43 @@ def write_centers_indices(path, indices, intermediate_n=None):
         np.save(f, indices)
 
 
+def load_asymm_frames(center_indices, trajectories, topologies, subsample):
+    """Full-topology structures of the cluster centres, re-loaded from the trajectory files at
+    ``(trajectory, frame * subsample)`` (util.py:407-431): what the reference pickles, ALL
+    atoms, not only the ``--atoms`` selection that was clustered."""
+    md, have_md = _traj_backend()
+    flat, tops = [], []
+    for topfile, trjset in zip(topologies, trajectories):
+        top = md.load(topfile).top if have_md else md.load_topology(topfile)
+        for trj in trjset:
+            flat.append(trj)
+            tops.append(top)
+    frames = []
+    for t, f in center_indices:
+        frames.append(md.load_frame(flat[int(t)], int(f) * int(subsample), top=tops[int(t)]))
+    return frames
+
+
 def write_centers(result, args, intermediate_n=None):
-    """Feature centres -> .npy; trajectory centres -> pickle of frames (util.py:481-508)."""
+    """Feature centres -> .npy; trajectory centres -> pickle of full-topology frames re-loaded
+    from the trajectory files (util.py:481-508)."""
     path = args.center_features
     if intermediate_n is not None:
         path = _intermediate_path(path, intermediate_n)
     if args.features:
         np.save(path, np.asarray(result.centers))
-    else:
-        with open(path, "wb") as f:
-            pickle.dump(result.centers, f)
+        return
+    try:
+        centers = load_asymm_frames(result.center_indices, args.trajectories, args.topologies,
+                                    args.subsample)
+    except ImproperlyConfigured as exc:
+        # a format neither mdtraj (absent) nor the native readers handle: keep the clustered
+        # (atom-sliced) frames rather than nothing, and say so
+        logger.warning("Could not re-load full centre structures (%s); writing the clustered "
+                       "atom selection instead.", exc)
+        centers = result.centers
+    with open(path, "wb") as f:
+        pickle.dump(centers, f)
 
 
 def write_assignments_and_distances(result, args, intermediate_n=None):

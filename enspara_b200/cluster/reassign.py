@@ -106,11 +106,14 @@ def sound_trajectory(path, stride=1):
     elif e in (".h5", ".hdf5"):
         from ..util import h5min
         n = h5min.File(path)["coordinates"].shape[0]
+    elif e == ".xtc":
+        from ..util import traj
+        n = traj.xtc_shape(path)[0]        # native: frame headers only
     else:
         md = _mdtraj()
         if md is None:
             raise ImproperlyConfigured(
-                "Reading '%s' needs mdtraj, which is not installed; .npy and mdtraj .h5 "
+                "Reading '%s' needs mdtraj, which is not installed; .xtc, .npy and mdtraj .h5 "
                 "trajectories are read natively." % path)
         with md.open(path) as f:
             n = len(f)
@@ -120,7 +123,14 @@ def sound_trajectory(path, stride=1):
 def load_frames(path, top=None, atom_indices=None, out=None):
     """(n, A, 3) float32 coordinates of one file, optionally into ``out``."""
     e = _ext(path)
-    if e == ".npy":
+    if e == ".xtc":
+        # native decoder: the atom selection is applied while decoding, straight into ``out``
+        from ..util import traj
+        if out is not None and out.flags.c_contiguous and out.dtype == np.float32:
+            return traj.read_xtc(path, atom_indices=atom_indices, out=out)
+        xyz = traj.read_xtc(path, atom_indices=atom_indices)
+        atom_indices = None
+    elif e == ".npy":
         xyz = np.load(path, mmap_mode="r")
     elif e in (".h5", ".hdf5"):
         from ..util import h5min
@@ -145,18 +155,26 @@ def load_frames(path, top=None, atom_indices=None, out=None):
 
 def _select_atoms(topfile, selection):
     """(topology object or None, atom indices or None) for one topology / selection pair."""
-    if selection is None or (isinstance(selection, str) and selection.strip() == "all"
-                             and _mdtraj() is None):
+    if selection is None:
         return None, None
     if not isinstance(selection, str):
         return None, np.asarray(selection, dtype=np.int64)
     md = _mdtraj()
-    if md is None:
+    if md is not None:
+        top = md.load(topfile).top
+        return top, top.select(selection)
+    if selection.strip() == "all" and (topfile is None or not os.path.exists(str(topfile))
+                                       or _ext(str(topfile)) not in (".pdb", ".ent")):
+        return None, None
+    # no mdtraj: .pdb topologies and the selection mini-language of util/traj.py
+    from ..util import traj
+    top = traj.load_topology(topfile)
+    try:
+        return top, top.select(selection)
+    except ValueError as exc:
         raise ImproperlyConfigured(
-            "Atom selection strings (%r) need mdtraj, which is not installed; pass index "
-            "arrays or 'all'." % selection)
-    top = md.load(topfile).top
-    return top, top.select(selection)
+            "The provided selection '%s' didn't match the topology file, %s (%s)"
+            % (selection, topfile, exc))
 
 
 def _centers_xyz(centers, n_atoms=None):

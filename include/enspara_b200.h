@@ -282,6 +282,17 @@ int eb_count_members(const int32_t *assign, int64_t n, int32_t k, int64_t *count
 int eb_select_member(const int32_t *assign, int64_t n, int32_t cid, int64_t kth, int64_t *out,
                      void *scratch, void *stream);
 
+/* ---- trajectory input without mdtraj: native GROMACS .xtc reader (host code) -------------
+ * Replaces md.load(path, stride=, atom_indices=) for .xtc files in the loaders either side of
+ * the hot path (cluster/util.py:350-404 load_trajectories, mpi/io.py:142-194
+ * load_trajectory_as_striped, the batch loader of cluster/util.py:584-649).  eb_xtc_scan walks
+ * the frame headers only.  eb_xtc_read decodes frames first, first+stride, ... (at most
+ * max_frames; < 0: all) into xyz_out[(frame, atom, 3)] float32 nanometres (HOST memory);
+ * atom_idx (n_sel indices, optional) selects and orders the atoms while decoding. */
+int eb_xtc_scan(const char *path, int64_t *n_frames, int32_t *n_atoms);
+int eb_xtc_read(const char *path, int64_t first, int64_t stride, int64_t max_frames,
+                const int32_t *atom_idx, int32_t n_sel, float *xyz_out, int64_t *n_read);
+
 /* ---- synthetic data: counter-based generator keyed on (seed, global frame) -
  * Writes centred SoA frames + traces directly in HBM so a 10M x 500-atom trajectory never has
  * to exist on the host.  The same generator is restated in numpy (enspara_b200/synth.py) for
