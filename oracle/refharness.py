@@ -70,6 +70,11 @@ def load():
     from . import distances as od
 
     so = build_libdist()
+    # load_compiled_libdist() may have registered a stub package: the real one replaces it
+    for name in [m for m in sys.modules if m == "enspara" or m.startswith("enspara.")]:
+        if getattr(sys.modules[name], "_eb_stub", False) or \
+                getattr(sys.modules.get("enspara"), "_eb_stub", False):
+            del sys.modules[name]
 
     md = types.ModuleType("mdtraj")
     md.rmsd = od.rmsd
@@ -120,6 +125,10 @@ def load_compiled_libdist():
     name = "enspara.geometry.libdist"
     if name in sys.modules and hasattr(sys.modules[name], "euclidean"):
         return sys.modules[name]
+    if available():
+        # build container: the real package is importable, no stub needed
+        load()
+        return sys.modules[name]
     hits = glob.glob(os.path.join(_GEOM_DIR, "libdist*.so"))
     if not hits:
         if not available():
@@ -129,6 +138,7 @@ def load_compiled_libdist():
     if "enspara" not in sys.modules:
         pkg = types.ModuleType("enspara")
         pkg.__path__ = []
+        pkg._eb_stub = True
         exc = types.ModuleType("enspara.exception")
 
         class ImproperlyConfigured(Exception):

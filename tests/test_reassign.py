@@ -44,7 +44,10 @@ def test_sound_and_load(tmp_path, frame0_h5_xyz):
     assert_array_equal(rz.load_frames(p_h5), frame0_h5_xyz[:30])
     sub = rz.load_frames(p_npy, atom_indices=[0, 3, 5])
     assert_array_equal(sub, frame0_h5_xyz[:40][:, [0, 3, 5]])
-    with pytest.raises(ImproperlyConfigured):
+    with pytest.raises(ImproperlyConfigured):      # a format only mdtraj reads
+        rz.sound_trajectory(str(tmp_path / "a.dcd"))
+    from enspara_b200.exception import DataInvalid
+    with pytest.raises(DataInvalid):                # .xtc is read natively: a missing file
         rz.sound_trajectory(str(tmp_path / "a.xtc"))
 
 
