@@ -50,6 +50,20 @@ def test_c4_shard_rmsd_full_size(cuda):
     s = kcenters.kcenters(X, "rmsd", dist_cutoff=radius)
     assert [int(i) for i in s.center_indices] == c
     assert s.distances.max() <= radius
+    # against the ORACLE (restated mdtraj RMSD, float64) on a sample: the brute-force nearest of
+    # the 96 centres equals the full-size run's assignment, distances to 1e-5
+    # (enspara/test/test_cluster_util.py:88-123)
+    from oracle import cluster as oc
+    from oracle import distances as od
+    od.use_all_cores()
+    pick = np.sort(np.random.RandomState(0).choice(n, 600, replace=False))
+    frames = X.gather(pick).to_host_aos()
+    cen_host = cen.to_host_aos()
+    oa, odist = oc.assign_to_nearest_center(
+        od.Trajectory(frames), [od.Trajectory(x[None]) for x in cen_host], od.rmsd)
+    np.testing.assert_allclose(r.distances[pick], odist, rtol=1e-5, atol=1e-6)
+    mism = np.nonzero(r.assignments[pick] != oa)[0]
+    assert len(mism) <= 1       # only a documented near-tie (< 1e-6 nm) may differ
 
 
 def test_c2_features_full_size(cuda):
@@ -98,3 +112,23 @@ def test_tma_staged_step_equals_ldg_step(cuda, A, monkeypatch):
     d1 = _ops.one_to_all_device(util.RMSD, X, X.gather(torch.as_tensor(c[-1:], device="cuda")))
     won = eng.assign == len(c) - 1
     assert torch.equal(d1[won], eng.dist[won]) and bool((d1[~won] >= eng.dist[~won]).all())
+
+
+def test_config2_full_size_bit_exact_against_the_oracle():
+    """BASELINE configs[1] at FULL size: KCenters euclidean on 1M x 64 float32 rows (the
+    persistent multi-iteration kernel), 40 centres, against the oracle's libdist restatement
+    (itself bit-identical to the reference's compiled Cython libdist, tests/test_oracle_ref.py):
+    centres, assignments and float64 distances must be EQUAL."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from enspara_b200.cluster import KCenters
+    from oracle import cluster as oc
+    from oracle import distances as od
+    od.use_all_cores()
+    X = od.synth_features(1_000_000, 64, seed=0)         # bit-identical to synth.features
+    ref = oc.kcenters(X, od.euclidean, n_clusters=40)
+    got = KCenters("euclidean", n_clusters=40).fit(X).result_
+    assert [int(c) for c in got.center_indices] == [int(c) for c in ref.center_indices]
+    np.testing.assert_array_equal(got.assignments, ref.assignments)
+    np.testing.assert_array_equal(got.distances, ref.distances)
