@@ -537,6 +537,79 @@ k_tc_screen(const unsigned char *__restrict__ a_img, const unsigned char *__rest
     }
 }
 
+// ---- load balance of the re-score: frames bucketed by their candidate count --------------------
+// A warp of the re-score kernel owns four frames and runs as many passes (two centres each) as
+// the frame with the most survivors needs.  On the synthetic ensemble neighbouring frames belong
+// to different conformers and their counts differ a lot: measured at 262144 x 1008, 3.7 passes
+// per frame on average but 8.3 per warp (x2.25).  A counting sort on min(63, passes) -- three
+// tiny launches -- puts frames with equal counts next to each other, largest first.
+constexpr int RS_BINS = 64;
+
+__global__ void __launch_bounds__(256)
+k_rs_key(const int *__restrict__ cand_count, const float *__restrict__ cand_bound,
+         const float *__restrict__ cand_umin, long n, int n_lists, int MAX_CAND,
+         unsigned char *key, int *hist)
+{
+    __shared__ int sh[RS_BINS];
+    if (threadIdx.x < RS_BINS) sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (long f = (long)blockIdx.x * blockDim.x + threadIdx.x; f < n;
+         f += (long)gridDim.x * blockDim.x) {
+        // exactly what the re-score will keep: entries whose lower bound does not exceed the
+        // frame's best upper bound over all lists
+        float U = INFINITY;
+        bool ovf = false;
+        for (int l = 0; l < n_lists; ++l) {
+            U = fminf(U, __ldg(cand_umin + (size_t)f * n_lists + l));
+            ovf |= __ldg(cand_count + (size_t)f * n_lists + l) < 0;
+        }
+        int tot = 0;
+        if (!ovf) {
+            for (int l = 0; l < n_lists; ++l) {
+                const int c = __ldg(cand_count + (size_t)f * n_lists + l);
+                const float *b = cand_bound + ((size_t)f * n_lists + l) * MAX_CAND;
+                for (int e = 0; e < c; ++e) tot += __ldg(b + e) <= U;
+            }
+        }
+        const int k = min(RS_BINS - 1, (tot + 1) >> 1);
+        key[f] = (unsigned char)k;
+        atomicAdd(&sh[k], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < RS_BINS && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+
+// one warp: offsets of the bins in DESCENDING key order; resets the cursors
+__global__ void k_rs_scan(const int *hist, int *offsets, int *cursor)
+{
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int k = RS_BINS - 1; k >= 0; --k) {
+            offsets[k] = run;
+            run += hist[k];
+            cursor[k] = 0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_rs_scatter(const unsigned char *__restrict__ key, long n, const int *__restrict__ offsets,
+             int *cursor, int *order)
+{
+    for (long f = (long)blockIdx.x * blockDim.x + threadIdx.x; f < n;
+         f += (long)gridDim.x * blockDim.x) {
+        const int k = key[f];
+        // warp-aggregated cursor bump per bin
+        const unsigned peers = __match_any_sync(__activemask(), k);
+        const int leader = __ffs(peers) - 1;
+        const int lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&cursor[k], __popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        order[offsets[k] + base + __popc(peers & ((1u << lane) - 1u))] = (int)f;
+    }
+}
+
 // ---- exact re-scoring of the surviving (frame, centre) pairs ---------------------------------
 // A group of 8 lanes owns one frame: it merges the frame's candidate lists (global upper bound
 // U = min over lists; survivors = entries whose lower bound does not exceed U) into one compact
@@ -557,7 +630,8 @@ k_rescore(const float *__restrict__ xyz, const double *__restrict__ traces, long
           const float *__restrict__ cand_bound, const float *__restrict__ cand_umin, int n_seg,
           float *out_dist, int *out_assign, int *frame_flag,
           const int64_t *__restrict__ frame_idx, int scatter, int MAX_CAND,
-          const int *__restrict__ f16_overflow, const int *__restrict__ n_dev, int *ovf_count)
+          const int *__restrict__ f16_overflow, const int *__restrict__ n_dev, int *ovf_count,
+          const int *__restrict__ order)
 {
     extern __shared__ __align__(16) unsigned char rs_smem[];
     if (n_dev) n = min(n, (long)__ldg(n_dev));
@@ -571,8 +645,10 @@ k_rescore(const float *__restrict__ xyz, const double *__restrict__ traces, long
     const long groups = (long)gridDim.x * RS_GROUPS;
     const long n_round = (n + groups - 1) / groups * groups;   // every warp runs the same trips
     for (long fb = (long)blockIdx.x * RS_GROUPS + grp; fb < n_round; fb += groups) {
-        const long f = fb;
-        const bool valid = f < n;
+        // `order` (optional): frames sorted by their number of candidates, so that the four
+        // frames of a warp need the same number of passes (the warp runs the maximum)
+        const bool valid = fb < n;
+        const long f = valid ? (order ? (long)__ldg(order + fb) : fb) : fb;
         // merge the lists: global upper bound, overflow if any list overflowed
         float U = INFINITY;
         int ovf = 0;
@@ -743,7 +819,7 @@ size_t eb_tc_scratch_bytes(int64_t n, int n_atoms, int32_t k)
            (size_t)n * n_lists *
                (sizeof(int) + sizeof(float) +
                 tc_max_cand((int)n_lists) * (sizeof(int) + sizeof(float))) +
-           4096;
+           (size_t)n * (sizeof(int) + 1) + 4096;   // + re-score order / keys, bins, flags
 }
 
 // mode 0 (debug): dbg receives the approximate inner-product matrices, n x k x 9 floats.
@@ -852,6 +928,23 @@ int eb_rmsd_assign_tc_dev(const float *xyz_soa, const double *traces, int64_t n,
                                                        cand_umin, n_seg, frame_idx, max_cand,
                                                        n_dev);
     EB_LAUNCH_CHECK();
+    // frames bucketed by candidate count (dense passes only: a few microseconds that a small
+    // PAM subset would not earn back, and its size is only known on the device)
+    int *order = nullptr;
+    if (!n_dev && n >= 16384 && n < (1L << 31)) {
+        int *bins = (int *)(((uintptr_t)(f16_overflow + 4) + 15) & ~(uintptr_t)15);   // 3 x 64
+        order = bins + 3 * tc::RS_BINS;
+        unsigned char *key = (unsigned char *)(order + n);
+        EB_CUDA(cudaMemsetAsync(bins, 0, sizeof(int) * tc::RS_BINS, s));
+        long kb = (n + 255) / 256;
+        if (kb > 8L * sm_count()) kb = 8L * sm_count();
+        tc::k_rs_key<<<(int)kb, 256, 0, s>>>(seg_count, cand_bound, cand_umin, n, (int)n_lists,
+                                             max_cand, key, bins);
+        tc::k_rs_scan<<<1, 32, 0, s>>>(bins, bins + tc::RS_BINS, bins + 2 * tc::RS_BINS);
+        tc::k_rs_scatter<<<(int)kb, 256, 0, s>>>(key, n, bins + tc::RS_BINS,
+                                                 bins + 2 * tc::RS_BINS, order);
+        EB_LAUNCH_CHECK();
+    }
     {
         const size_t rs_smem = align16(sizeof(int) * tc::RS_GROUPS * n_lists * max_cand);
         long blocks = (n + tc::RS_GROUPS - 1) / tc::RS_GROUPS;
@@ -862,7 +955,7 @@ int eb_rmsd_assign_tc_dev(const float *xyz_soa, const double *traces, int64_t n,
         tc::k_rescore<<<(int)blocks, tc::RS_THREADS, rs_smem, s>>>(
             xyz_soa, traces, n, n_atoms, A_pad, centers_soa, center_traces, seg_count, cand_list,
             cand_bound, cand_umin, (int)n_lists, out_dist, out_assign, cand_count, frame_idx,
-            scatter, max_cand, f16_overflow, n_dev, overflow_count);
+            scatter, max_cand, f16_overflow, n_dev, overflow_count, order);
         EB_LAUNCH_CHECK();
     }
     return EB_OK;
@@ -896,7 +989,7 @@ int eb_rmsd_score_lists(const float *xyz_soa, const double *traces, int64_t n_po
     tc::k_rescore<<<(int)blocks, tc::RS_THREADS, rs_smem, (cudaStream_t)stream>>>(
         xyz_soa, traces, n_pos, n_atoms, rmsd_apad(n_atoms), centers_soa, center_traces,
         cand_count, cand_list, bound_lo, bound_up, 1, out_dist, out_assign, frame_flag, frame_idx,
-        0, list_len, zero_flag, nullptr, nullptr);
+        0, list_len, zero_flag, nullptr, nullptr, nullptr);
     EB_LAUNCH_CHECK();
     return EB_OK;
 }

@@ -38,6 +38,15 @@ for name, kappa in (("rigorous", _ops.tc_kappa(data.a_pad)), ("round1_8x", 8 * 2
     for e in prof.key_averages():
         times[e.key.split("(")[0][-40:]] = round(e.device_time_total / e.count / 1e3, 3)
     surv = float(cand.clamp(min=0).float().mean())
+    if name == "rigorous":
+        c = cand.clamp(min=0)
+        passes = (c + 1) // 2
+        per_warp = passes.view(-1, 4).max(dim=1).values.float().mean()
+        q = torch.quantile(c.float()[::64], torch.tensor([0.5, 0.9, 0.99, 1.0], device="cuda"))
+        print("re-score load balance: mean passes per frame %.2f, mean of max over a warp's 4 "
+              "frames %.2f (x%.2f); survivors p50/p90/p99/max = %s"
+              % (float(passes.float().mean()), float(per_warp),
+                 float(per_warp) / float(passes.float().mean()), q.tolist()), flush=True)
     ovf = int((cand < 0).sum())
     out[name] = {"kappa": kappa, "kernel_ms": times, "survivors_per_frame": surv, "overflow": ovf}
     print(name, json.dumps(out[name]), flush=True)
