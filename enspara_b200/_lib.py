@@ -78,6 +78,7 @@ SIGNATURES = {
     "eb_feat_assign": (_int, [_vp, _i64, _i64, _int, _int, _vp, _i32, _vp, _i64, _vp, _vp,
                               _int, _int, _vp]),
     "eb_pam_classify": (_int, [_vp, _vp, _vp, _i64, _int, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "eb_pam_need_list": (_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "eb_pam_scratch_bytes": (_sz, [_i64]),
     "eb_sum_squares": (_int, [_vp, _i64, _int, _vp, _vp, _vp]),
     "eb_count_members": (_int, [_vp, _i64, _i32, _vp, _vp]),

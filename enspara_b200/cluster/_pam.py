@@ -72,6 +72,12 @@ class PamEngine:
         # stay with their medoid are not read; the sweep's result is unchanged
         self.prune = self.is_rmsd and self.k >= 2
         self.cc = torch.zeros(max(self.k, 1), dtype=torch.float32, device=dev)
+        #: compact-list form of the pruned pass (default) vs the fused skip-rounds kernel
+        self.prune_compact = True
+        if self.prune:
+            self.need_idx = torch.empty(max(self.n, 1), dtype=torch.int64, device=dev)
+            self.need_n = torch.zeros(1, dtype=torch.int64, device=dev)
+            self.need_assign = torch.zeros(max(self.n, 1), dtype=torch.int32, device=dev)
         self.counts_by_rank = None
         self._proposals_done = 0
         # pinned landing zone of the one read-back per proposal: [cost], [proposal, n_ambig],
@@ -277,10 +283,22 @@ class PamEngine:
                 # distances proposal -> every medoid (k evaluations), then the pruned pass
                 _ops.one_to_all_device(self.metric, self.medoids, self.prop, out=self.cc)
                 d = self.new_ctr_dist
-                _lib.call("eb_rmsd_one_to_all_pruned", ptr(self.data.xyz),
-                          ptr(self.data.traces), self.n, self.data.n_atoms, ptr(self.prop.xyz),
-                          ptr(self.prop.traces), ptr(self.dist), ptr(self.assign), ptr(self.cc),
-                          cid, ptr(d), stream_ptr())
+                if self.prune_compact:
+                    # frames that provably keep their medoid get +inf; the rest, as a compact
+                    # list, are evaluated against the proposal by the exact kernel (k = 1) with
+                    # every lane busy; same values as the fused pruned pass / a full pass
+                    _lib.call("eb_pam_need_list", ptr(self.dist), ptr(self.assign), ptr(self.cc),
+                              self.n, cid, ptr(d), ptr(self.need_idx), ptr(self.need_n),
+                              stream_ptr())
+                    _ops.assign_device(self.metric, self.data, self.prop,
+                                       frame_idx=self.need_idx, n_idx=self.n, out_dist=d,
+                                       out_assign=self.need_assign, accumulate=False,
+                                       scatter=True, k=1, n_dev=self.need_n)
+                else:
+                    _lib.call("eb_rmsd_one_to_all_pruned", ptr(self.data.xyz),
+                              ptr(self.data.traces), self.n, self.data.n_atoms,
+                              ptr(self.prop.xyz), ptr(self.prop.traces), ptr(self.dist),
+                              ptr(self.assign), ptr(self.cc), cid, ptr(d), stream_ptr())
             else:
                 d = _ops.one_to_all_device(self.metric, self.data, self.prop,
                                            out=self.new_ctr_dist)

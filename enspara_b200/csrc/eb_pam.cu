@@ -55,6 +55,39 @@ k_pam_classify(const D *__restrict__ new_ctr_dist, const D *__restrict__ dist,
     }
 }
 
+// Triangle-inequality pre-pass of a PAM proposal's full distance pass (kmedoids.py:637): a frame
+// of ANOTHER cluster whose distance to its medoid is at most (1 - 1e-5)/2 of that medoid's
+// distance to the proposal (cc[assign]) cannot get closer to the proposal than it is to its
+// medoid, so the three-way split leaves it untouched: it gets +inf and is never read.  Every
+// other frame goes to a compact index list; the exact kernel then evaluates the proposal
+// against exactly those frames with all its lanes busy (the fused pruned pass of round 1
+// skipped 4-frame rounds inside 32-frame chunks: with ~3 % of the frames scattered over the
+// shard almost every round still had one live frame and three idle groups).
+__global__ void __launch_bounds__(kPamThreads)
+k_pam_need_list(const float *__restrict__ dist, const int *__restrict__ assign,
+                const float *__restrict__ cc, long n, int cid, float *__restrict__ out,
+                int64_t *__restrict__ need_idx, unsigned long long *n_need)
+{
+    const int lane = threadIdx.x & 31;
+    const long stride = (long)gridDim.x * blockDim.x;
+    const long n_round = (n + 31) & ~31L;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        bool need = false;
+        if (i < n) {
+            const int a = assign[i];
+            need = (a < 0) || (a == cid) || !(dist[i] <= 0.499995f * __ldg(cc + a));
+            if (!need) out[i] = INFINITY;
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, need);
+        if (mask) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(n_need, (unsigned long long)__popc(mask));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (need) need_idx[base + __popc(mask & ((1u << lane) - 1))] = i;
+        }
+    }
+}
+
 // deterministic sum of squares: fixed block ranges, fixed tree, ordered final pass
 template <typename D>
 __global__ void __launch_bounds__(kPamThreads)
@@ -239,6 +272,20 @@ int eb_pam_classify(const void *new_ctr_dist, const void *dist, const int32_t *a
         k_pam_classify<float><<<pam_blocks(n), kPamThreads, 0, s>>>(
             (const float *)new_ctr_dist, (const float *)dist, assign, n, cid, (float *)new_dist,
             new_assign, ambig_idx, (unsigned long long *)n_ambig);
+    EB_LAUNCH_CHECK();
+    return EB_OK;
+}
+
+int eb_pam_need_list(const float *dist, const int32_t *assign, const float *cc, int64_t n,
+                     int32_t cid, float *out, int64_t *need_idx, int64_t *n_need, void *stream)
+{
+    EB_CHECK_ARG(n >= 0 && n_need, "pam_need_list: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    EB_CUDA(cudaMemsetAsync(n_need, 0, sizeof(int64_t), s));
+    if (n == 0) return EB_OK;
+    EB_CHECK_ARG(dist && assign && cc && out && need_idx, "pam_need_list: null pointer");
+    k_pam_need_list<<<pam_blocks(n), kPamThreads, 0, s>>>(dist, assign, cc, n, cid, out, need_idx,
+                                                         (unsigned long long *)n_need);
     EB_LAUNCH_CHECK();
     return EB_OK;
 }

@@ -275,6 +275,15 @@ int eb_feat_assign(const void *X, int64_t n, int64_t n_features, int dtype, int 
 int eb_pam_classify(const void *new_ctr_dist, const void *dist, const int32_t *assign, int64_t n,
                     int dist_is_f64, int32_t cid, void *new_dist, int32_t *new_assign,
                     int64_t *ambig_idx, int64_t *n_ambig, void *stream);
+/* Triangle-inequality pre-pass of a proposal's full distance pass (kmedoids.py:637; RMSD is a
+ * metric): with cc[j] = d(proposal, medoid j), a frame of another cluster with
+ * dist <= (1 - 1e-5)/2 * cc[assign] provably keeps its medoid -- out[f] = +inf, never read --
+ * every other frame index goes to need_idx (compact, unordered), *n_need receives their number.
+ * The caller evaluates the proposal against exactly those frames (eb_rmsd_assign_dev, k = 1,
+ * scattered output), so the split of kmedoids.py:644-658 sees the same values as after a full
+ * pass. */
+int eb_pam_need_list(const float *dist, const int32_t *assign, const float *cc, int64_t n,
+                     int32_t cid, float *out, int64_t *need_idx, int64_t *n_need, void *stream);
 size_t eb_pam_scratch_bytes(int64_t n);
 int eb_sum_squares(const void *dist, int64_t n, int dist_is_f64, double *out, void *scratch,
                    void *stream);

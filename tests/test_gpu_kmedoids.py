@@ -238,19 +238,22 @@ def test_pam_pruned_full_pass_changes_nothing(cuda):
         r = kcenters.kcenters(data, "rmsd", n_clusters=k)
         ctr = [int(c) for c in r.center_indices]
         out = []
-        for prune in (True, False):
+        for prune, compact in ((True, True), (True, False), (False, False)):
+            # compact-list pruned pass (default), fused skip-rounds pruned pass, full pass
             pam = PamEngine(data, util.RMSD, _SingleComm(), r.distances, r.assignments, ctr)
-            assert pam.prune
+            assert pam.prune and pam.prune_compact
             pam.prune = prune
+            pam.prune_compact = compact
             log = []
             for sweep in range(2):
                 pam.sweep(random_state=sweep, log=log)
             a, d = pam.results_host()
             out.append((list(pam.medoid_global), a, d, log))
-        assert out[0][0] == out[1][0]
-        assert_array_equal(out[0][1], out[1][1])
-        assert_array_equal(out[0][2], out[1][2])
-        assert out[0][3] == out[1][3]        # same proposals, same costs, same decisions
+        for other in out[1:]:
+            assert out[0][0] == other[0]
+            assert_array_equal(out[0][1], other[1])
+            assert_array_equal(out[0][2], other[2])
+            assert out[0][3] == other[3]     # same proposals, same costs, same decisions
 
 
 def test_kmedoids_update_mpi_numpy_golden(cuda):
