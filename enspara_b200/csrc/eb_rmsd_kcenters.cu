@@ -599,7 +599,12 @@ k_kcenters_multi_rmsd(const float *__restrict__ xyz, const double *__restrict__ 
 // S: ring depth (S - 1 stages are in flight while one is consumed).
 // MODE: kModeStep (the k-centers iteration) or kModeDistOnly (md.rmsd(X, y): the centre comes
 // from center_direct / center_trace_direct and out_only[f] receives the distance).
-template <int P, int S, int MODE = kModeStep>
+// FR: frames per 8-lane group and stage (1 or 2).  With FR = 2 a stage holds EIGHT frames (box of
+// 24 rows) and a group accumulates two of them against ONE read of the float64 centre from
+// shared memory: 12 instead of 18 LDS.128 per two frames (ncu had the L1TEX data pipe at 65 %,
+// two thirds of it the centre).  Each frame's own summation order is unchanged, so results stay
+// bit-identical.
+template <int P, int S, int MODE = kModeStep, int FR = 1>
 __global__ void __launch_bounds__(kStepThreads, 1)
 k_kcenters_step_rmsd_tma(const float *__restrict__ xyz, const double *__restrict__ traces, long n,
                          int A, int A_pad, long frame_offset, const unsigned char *cand_in,
@@ -610,9 +615,10 @@ k_kcenters_step_rmsd_tma(const float *__restrict__ xyz, const double *__restrict
                          const double *center_trace_direct, float *out_only, Exch exch)
 {
     extern __shared__ __align__(128) unsigned char smem_tma[];
-    constexpr int kStagesPerChunk = 8 * P;                       // 8 rounds x P parts
+    constexpr int kFPR = 4 * FR;                                 // frames per round (= stage)
+    constexpr int kStagesPerChunk = (32 / kFPR) * P;             // rounds x P parts
     const uint32_t part_row_bytes = 4u * (uint32_t)A_pad / P;    // one part of a coordinate row
-    const uint32_t stage_bytes = 12u * part_row_bytes;           // 4 frames x 3 rows
+    const uint32_t stage_bytes = 3u * kFPR * part_row_bytes;     // kFPR frames x 3 rows
     unsigned char *ring = smem_tma;                              // [warps][S][stage_bytes]
     uint64_t *bars = reinterpret_cast<uint64_t *>(ring + (size_t)kStepWarps * S * stage_bytes);
     StepSmem *ss = reinterpret_cast<StepSmem *>(bars + kStepWarps * S);
@@ -702,7 +708,7 @@ k_kcenters_step_rmsd_tma(const float *__restrict__ xyz, const double *__restrict
     unsigned q_issue = 0;
     auto issue = [&]() {
         if (i_chunk < n_chunks) {
-            const long f0 = (i_chunk << 5) + 4 * (i_st / P);
+            const long f0 = (i_chunk << 5) + kFPR * (i_st / P);
             if (lane == 0 && f0 < n) {
                 const int b = (int)(q_issue % S);
                 mbar_expect_tx(&bar[b], stage_bytes);
@@ -723,7 +729,7 @@ k_kcenters_step_rmsd_tma(const float *__restrict__ xyz, const double *__restrict
     for (long chunk = (long)blockIdx.x * kStepWarps + warp; chunk < n_chunks;
          chunk += warps_total) {
         const long base = chunk << 5;
-        double m[9];
+        double m[9], m2[9];
 #pragma unroll 1
         for (int st = 0; st < kStagesPerChunk; ++st, ++q) {
             const int b = (int)(q % S);
@@ -731,15 +737,19 @@ k_kcenters_step_rmsd_tma(const float *__restrict__ xyz, const double *__restrict
             // the buffer consumed in the previous stage is free (all lanes are past its
             // __syncwarp): request the stage S - 1 ahead into it
             issue();
-            const long f0 = base + 4 * (st / P);
+            const long f0 = base + kFPR * (st / P);
             if (f0 < n) mbar_wait(&bar[b], (q / S) & 1u);
             if (part == 0) {
 #pragma unroll
                 for (int e = 0; e < 9; ++e) m[e] = 0.0;
+                if (FR == 2) {
+#pragma unroll
+                    for (int e = 0; e < 9; ++e) m2[e] = 0.0;
+                }
             }
             const long fs = f0 + g;
             if (fs < n) {
-                // rows of this group's frame in the stage: pitch = one part of a row
+                // rows of this group's frame(s) in the stage: pitch = one part of a row
                 const float4 *px = reinterpret_cast<const float4 *>(
                     my_ring + (size_t)b * stage_bytes + (size_t)(3 * g) * part_row_bytes);
                 const float4 *py = px + A4p;
@@ -747,25 +757,56 @@ k_kcenters_step_rmsd_tma(const float *__restrict__ xyz, const double *__restrict
                 const int lo = part * A4p, hi = lo + A4p;
                 // first j >= lo with j == l8 (mod 8): the LDG kernel's per-lane order
                 int j = lo + ((l8 - lo) & 7);
+                if (FR == 1) {
 #pragma unroll 2
-                for (; j < hi; j += 8) {
-                    const int jj = j - lo;
-                    const float4 x = px[jj], y = py[jj], z = pz[jj];
-                    const double2 cxl = cs.lo[0][j], cxh = cs.hi[0][j];
-                    const double2 cyl = cs.lo[1][j], cyh = cs.hi[1][j];
-                    const double2 czl = cs.lo[2][j], czh = cs.hi[2][j];
-                    acc_atom(m, x.x, y.x, z.x, cxl.x, cyl.x, czl.x);
-                    acc_atom(m, x.y, y.y, z.y, cxl.y, cyl.y, czl.y);
-                    acc_atom(m, x.z, y.z, z.z, cxh.x, cyh.x, czh.x);
-                    acc_atom(m, x.w, y.w, z.w, cxh.y, cyh.y, czh.y);
+                    for (; j < hi; j += 8) {
+                        const int jj = j - lo;
+                        const float4 x = px[jj], y = py[jj], z = pz[jj];
+                        const double2 cxl = cs.lo[0][j], cxh = cs.hi[0][j];
+                        const double2 cyl = cs.lo[1][j], cyh = cs.hi[1][j];
+                        const double2 czl = cs.lo[2][j], czh = cs.hi[2][j];
+                        acc_atom(m, x.x, y.x, z.x, cxl.x, cyl.x, czl.x);
+                        acc_atom(m, x.y, y.y, z.y, cxl.y, cyl.y, czl.y);
+                        acc_atom(m, x.z, y.z, z.z, cxh.x, cyh.x, czh.x);
+                        acc_atom(m, x.w, y.w, z.w, cxh.y, cyh.y, czh.y);
+                    }
+                } else {
+                    // second frame of the group: four frames (12 rows) further down the stage;
+                    // rows past the last frame were zero-filled by the TMA unit
+                    const float4 *qx = px + 12 * A4p;
+                    const float4 *qy = qx + A4p;
+                    const float4 *qz = qy + A4p;
+#pragma unroll 2
+                    for (; j < hi; j += 8) {
+                        const int jj = j - lo;
+                        const float4 x = px[jj], y = py[jj], z = pz[jj];
+                        const float4 u = qx[jj], v = qy[jj], w = qz[jj];
+                        const double2 cxl = cs.lo[0][j], cxh = cs.hi[0][j];
+                        const double2 cyl = cs.lo[1][j], cyh = cs.hi[1][j];
+                        const double2 czl = cs.lo[2][j], czh = cs.hi[2][j];
+                        acc_atom(m, x.x, y.x, z.x, cxl.x, cyl.x, czl.x);
+                        acc_atom(m, x.y, y.y, z.y, cxl.y, cyl.y, czl.y);
+                        acc_atom(m, x.z, y.z, z.z, cxh.x, cyh.x, czh.x);
+                        acc_atom(m, x.w, y.w, z.w, cxh.y, cyh.y, czh.y);
+                        acc_atom(m2, u.x, v.x, w.x, cxl.x, cyl.x, czl.x);
+                        acc_atom(m2, u.y, v.y, w.y, cxl.y, cyl.y, czl.y);
+                        acc_atom(m2, u.z, v.z, w.z, cxh.x, cyh.x, czh.x);
+                        acc_atom(m2, u.w, v.w, w.w, cxh.y, cyh.y, czh.y);
+                    }
                 }
             }
             if (part == P - 1) {
                 group8_reduce(m);
+                if (FR == 2) group8_reduce(m2);
                 if (l8 == 0) {
-                    double *dst = my_sums + (4 * (st / P) + g) * kSumStride;
+                    double *dst = my_sums + (kFPR * (st / P) + g) * kSumStride;
 #pragma unroll
                     for (int e = 0; e < 9; ++e) dst[e] = m[e];
+                    if (FR == 2) {
+                        double *dst2 = dst + 4 * kSumStride;
+#pragma unroll
+                        for (int e = 0; e < 9; ++e) dst2[e] = m2[e];
+                    }
                 }
             }
             __syncwarp();
@@ -822,9 +863,9 @@ k_kcenters_step_rmsd_tma(const float *__restrict__ xyz, const double *__restrict
     if (exch.peers) exch_publish(exch, cand_out, rec_len);
 }
 
-static size_t step_tma_smem_bytes(int A_pad, int P, int S)
+static size_t step_tma_smem_bytes(int A_pad, int P, int S, int FR = 1)
 {
-    return (size_t)kStepWarps * S * 12 * (4 * (size_t)A_pad / P) +
+    return (size_t)kStepWarps * S * 12 * FR * (4 * (size_t)A_pad / P) +
            sizeof(uint64_t) * kStepWarps * S + align16(sizeof(StepSmem)) +
            sizeof(double) * kStepWarps * 32 * kSumStride + sizeof(double) * 3 * (size_t)A_pad;
 }
@@ -1136,15 +1177,34 @@ static int step_rmsd_impl(const float *xyz_soa, const double *traces, int64_t n,
     const int A_pad_ = rmsd_apad(n_atoms);
     int P = 1, S = 2;
     const bool use_tma = exact && step_uses_tma(n, n_atoms) && tma_config(A_pad_, &P, &S);
-    const size_t tma_smem = step_tma_smem_bytes(A_pad_, P, S);
+    // two frames per 8-lane group and centre read (FR = 2): stages of eight frames x 128 atoms
+    // (24 rows x 512 bytes = 12 KB), for rows of 256 / 384 / 512 floats.  EB_K1_FR=1 forces the
+    // one-frame form (developer A/B switch).
+    static const int fr_env = [] {
+        const char *e = getenv("EB_K1_FR");
+        return e ? atoi(e) : 2;
+    }();
+    int FR = 1;
+    if (use_tma && fr_env == 2 && A_pad_ % 128 == 0 && A_pad_ / 128 >= 2 && A_pad_ / 128 <= 4 &&
+        step_tma_smem_bytes(A_pad_, A_pad_ / 128, 2, 2) <= 227 * 1024) {
+        FR = 2;
+        P = A_pad_ / 128;
+        S = 2;
+    }
+    const size_t tma_smem = step_tma_smem_bytes(A_pad_, P, S, FR);
     if (use_tma) {
         CUtensorMap tmap;
         const int trc = make_tmap_2d(&tmap, xyz_soa, CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                                      sizeof(float), (uint64_t)(3 * n), (uint64_t)A_pad_,
-                                     (uint64_t)A_pad_ * sizeof(float), 12,
+                                     (uint64_t)A_pad_ * sizeof(float), 12 * FR,
                                      (uint32_t)(A_pad_ / P), CU_TENSOR_MAP_SWIZZLE_NONE);
         if (trc != EB_OK) return trc;
         auto kern = tma_kernel<kModeStep>(P, S);
+        if (FR == 2) {
+            kern = k_kcenters_step_rmsd_tma<2, 2, kModeStep, 2>;
+            if (P == 3) kern = k_kcenters_step_rmsd_tma<3, 2, kModeStep, 2>;
+            if (P == 4) kern = k_kcenters_step_rmsd_tma<4, 2, kModeStep, 2>;
+        }
         EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)tma_smem));
         const size_t rec_bytes = sizeof(RecHeader) + sizeof(float) * 3 * (size_t)A_pad_;
