@@ -387,7 +387,7 @@ k_kcenters_multi_feat(const T *__restrict__ X, long n, long F, long frame_offset
                       unsigned char *cand, size_t rec_bytes, double *dist, int *assign,
                       int n_clusters_limit, double cutoff, eb_kc_state *state,
                       int64_t *center_list, Partial *partials, unsigned long long *gbar,
-                      int n_steps, const __grid_constant__ CUtensorMap tmap)
+                      int n_steps, const __grid_constant__ CUtensorMap tmap, unsigned int *dyn)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *tiles = smem_raw;
@@ -421,9 +421,53 @@ k_kcenters_multi_feat(const T *__restrict__ X, long n, long F, long frame_offset
     unsigned char *tile = tiles + (size_t)warp * 2 * kTmaTileBytes;
     uint64_t *bar = bars + 2 * warp;
 
+    // Work distribution.  The body is HBM-fair only to a few per cent: with a purely static
+    // split block 0 waited 7-8 us per iteration for the slowest SM (measured).  So the first
+    // 7/8 of every warp's chunks are static (stride warps_total: the TMA ring can run ahead,
+    // also across the arg-max barrier) and the last eighth of the shard is handed out
+    // dynamically, one chunk per ticket of a global counter (dyn[iteration & 1]; block 0 resets
+    // the other one while nobody uses it).  Tickets only grow, so every lane still meets its
+    // rows in increasing order and the first-occurrence arg-max rule holds.
+    const long per_warp_static = (n_chunks * 7 / 8) / warps_total;
+    const bool dynamic_tail = per_warp_static >= 4;
+    const long n_static = dynamic_tail ? per_warp_static * warps_total : 0;
     // producer cursor: (iteration, chunk, tile); runs at most two tiles ahead of the consumer
     int p_iter = 0, p_jt = 0, p_buf = 0, inflight = 0;
-    long p_chunk = first_chunk;
+    long p_slot = 0;                    // static chunks already issued in iteration p_iter
+    long p_chunk = first_chunk;         // chunk being issued (valid while p_iter < n_steps)
+    long ticket = -1;                   // prefetched dynamic ticket (-1: none)
+    long buf_chunk[2] = {0, 0};
+    int buf_iter[2] = {-1, -1};
+    auto fetch_ticket = [&](int iter) {
+        unsigned int t = 0;
+        if (lane == 0) t = atomicAdd(&dyn[iter & 1], 1u);
+        return n_static + (long)__shfl_sync(0xffffffffu, t, 0);
+    };
+    // chunk after the one just issued; moves on to the next iteration when this one is done
+    auto advance_chunk = [&]() {
+        if (!dynamic_tail) {
+            p_chunk += warps_total;
+            if (p_chunk >= n_chunks) {
+                p_chunk = first_chunk;
+                ++p_iter;
+            }
+            return;
+        }
+        if (++p_slot < per_warp_static) {
+            p_chunk = first_chunk + p_slot * warps_total;
+            return;
+        }
+        const long t = ticket >= 0 ? ticket : fetch_ticket(p_iter);
+        if (t < n_chunks) {
+            p_chunk = t;
+            ticket = fetch_ticket(p_iter);      // needed at the next advance: latency hidden
+        } else {
+            ticket = -1;
+            p_slot = 0;
+            p_chunk = first_chunk;
+            ++p_iter;
+        }
+    };
     auto try_issue = [&]() {
         if (!has_work || p_iter >= n_steps || inflight >= 2) return;
         if (lane == 0) {
@@ -436,15 +480,13 @@ k_kcenters_multi_feat(const T *__restrict__ X, long n, long F, long frame_offset
                 tma_load_2d(dst + b * kBoxBytes, &tmap, (int)(j0 + (long)b * EPB),
                             (int)(p_chunk << 5), bar + p_buf);
         }
+        buf_chunk[p_buf] = p_chunk;
+        buf_iter[p_buf] = p_iter;
         p_buf ^= 1;
         ++inflight;
         if (++p_jt == nt) {
             p_jt = 0;
-            p_chunk += warps_total;
-            if (p_chunk >= n_chunks) {
-                p_chunk = first_chunk;
-                ++p_iter;
-            }
+            advance_chunk();
         }
     };
     uint32_t phase0 = 0, phase1 = 0;
@@ -513,36 +555,42 @@ k_kcenters_multi_feat(const T *__restrict__ X, long n, long F, long frame_offset
         double best_d = -2.0;
         int64_t best_i = INT64_MAX;
         double acc = 0.0;
-        for (long c_chunk = first_chunk; c_chunk < n_chunks; c_chunk += warps_total) {
-            for (int c_jt = 0; c_jt < nt; ++c_jt) {
-                try_issue();
-                wait_tile();
-                const long j0 = (long)c_jt * EPT;
-                const int fe = (int)min((long)EPT, F - j0);
-                acc = tile_terms_swz<T, METRIC>(acc, tile + c_buf * kTmaTileBytes, lane, y_sh, j0,
-                                                fe);
-                if (c_jt == nt - 1) {
-                    const long row = (c_chunk << 5) + lane;
-                    if (row < n) {
-                        const double d = finish<METRIC>(acc);
-                        const double old = dist[row];
-                        if (d < old) {  // strict '<', kcenters.py:304
-                            dist[row] = d;
-                            assign[row] = k;
-                        }
-                        const double cur = (d < old) ? d : old;
-                        if (cur > best_d) {
-                            best_d = cur;
-                            best_i = row;
-                        }
+        if (dynamic_tail && blockIdx.x == 0 && threadIdx.x == 0) dyn[(it + 1) & 1] = 0u;
+        int c_jt = 0;
+        for (;;) {
+            try_issue();
+            // this iteration is over for the warp when the next tile in the ring belongs to
+            // the following iteration, or nothing is left to request
+            if (inflight == 0 || buf_iter[c_buf] != it) break;
+            wait_tile();
+            const long c_chunk = buf_chunk[c_buf];
+            const long j0 = (long)c_jt * EPT;
+            const int fe = (int)min((long)EPT, F - j0);
+            acc = tile_terms_swz<T, METRIC>(acc, tile + c_buf * kTmaTileBytes, lane, y_sh, j0,
+                                            fe);
+            if (c_jt == nt - 1) {
+                const long row = (c_chunk << 5) + lane;
+                if (row < n) {
+                    const double d = finish<METRIC>(acc);
+                    // L2 reads: a dynamically assigned chunk may have been updated by another
+                    // SM in the previous iteration (L1 is not coherent across SMs)
+                    const double old = __ldcg(dist + row);
+                    if (d < old) {  // strict '<', kcenters.py:304
+                        dist[row] = d;
+                        assign[row] = k;
                     }
-                    acc = 0.0;
+                    const double cur = (d < old) ? d : old;
+                    if (cur > best_d) {
+                        best_d = cur;
+                        best_i = row;
+                    }
                 }
-                c_buf ^= 1;
-                --inflight;
-                __syncwarp();  // everyone is done with this buffer before it is refilled
-                try_issue();
+                acc = 0.0;
             }
+            if (++c_jt == nt) c_jt = 0;
+            c_buf ^= 1;
+            --inflight;
+            __syncwarp();  // everyone is done with this buffer before it is refilled
         }
         // ---- shard arg-max: per-block partial, grid barrier ------------------------------------
         if (blockIdx.x == 0 && threadIdx.x == 0) t_body_end = globaltimer_ns();
@@ -833,7 +881,7 @@ static int launch_feat_multi(const void *X, long n, long F, long frame_offset, v
     int grid = feat_grid(n, smem);
     const long cap = (long)per_sm * sm_count();
     if (grid > cap) grid = (int)cap;
-    if (2 * grid > kMaxGrid) return EB_OK;       // two partial buffers of `grid` entries
+    if (2 * grid + 1 > kMaxGrid) return EB_OK;   // two partial buffers of `grid` entries + tickets
     CUtensorMap tmap;
     const int rc = make_tmap_2d(&tmap, X, tmap_dtype<T>(), sizeof(T), (uint64_t)n, (uint64_t)F,
                                 (uint64_t)F * sizeof(T), 32, (uint32_t)(128 / sizeof(T)),
@@ -844,8 +892,11 @@ static int launch_feat_multi(const void *X, long n, long F, long frame_offset, v
     size_t rec_bytes = sizeof(RecHeader) + align16((size_t)F * sizeof(T));
     Partial *pp = (Partial *)partials;
     unsigned long long *gbar = reinterpret_cast<unsigned long long *>(&state->reserved);
+    // two ticket counters of the dynamic tail live behind the two partial buffers
+    unsigned int *dyn = reinterpret_cast<unsigned int *>(pp + 2 * (size_t)grid);
+    EB_CUDA(cudaMemsetAsync(dyn, 0, 2 * sizeof(unsigned int), stream));
     void *args[] = {&Xp, &n, &F, &frame_offset, &candp, &rec_bytes, &dist, &assign, &limit,
-                    &cutoff, &state, &center_list, &pp, &gbar, &n_steps, &tmap};
+                    &cutoff, &state, &center_list, &pp, &gbar, &n_steps, &tmap, &dyn};
     EB_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(kFeatThreads), args,
                                         smem, stream));
     *used = 1;
