@@ -1178,15 +1178,19 @@ static int step_rmsd_impl(const float *xyz_soa, const double *traces, int64_t n,
     int P = 1, S = 2;
     const bool use_tma = exact && step_uses_tma(n, n_atoms) && tma_config(A_pad_, &P, &S);
     // two frames per 8-lane group and centre read (FR = 2): stages of eight frames x 128 atoms
-    // (24 rows x 512 bytes = 12 KB), for rows of 256 / 384 / 512 floats.  EB_K1_FR=1 forces the
-    // one-frame form (developer A/B switch).
+    // (24 rows x 512 bytes = 12 KB).  Measured with bench.py's data at 1.25M frames, FR 1 -> 2:
+    // 256-float rows 0.604 -> 0.596 ms, 384 0.877 -> 0.854 ms, but 512-float rows 1.110 ->
+    // 1.135 ms (four 512-byte parts instead of two 1 KB parts: big copies win), so 512 keeps
+    // FR = 1.  EB_K1_FR=1 / 2 forces a form where it applies (developer A/B switch).
     static const int fr_env = [] {
         const char *e = getenv("EB_K1_FR");
-        return e ? atoi(e) : 2;
+        return e ? atoi(e) : 0;
     }();
     int FR = 1;
-    if (use_tma && fr_env == 2 && A_pad_ % 128 == 0 && A_pad_ / 128 >= 2 && A_pad_ / 128 <= 4 &&
-        step_tma_smem_bytes(A_pad_, A_pad_ / 128, 2, 2) <= 227 * 1024) {
+    const int parts128 = A_pad_ / 128;
+    const bool fr2_ok = use_tma && A_pad_ % 128 == 0 && parts128 >= 2 && parts128 <= 4 &&
+                        step_tma_smem_bytes(A_pad_, parts128, 2, 2) <= 227 * 1024;
+    if (fr2_ok && (fr_env == 2 || (fr_env == 0 && parts128 <= 3))) {
         FR = 2;
         P = A_pad_ / 128;
         S = 2;
