@@ -36,18 +36,35 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
-    """Compile every .cu under csrc/ into enspara_b200/libenspara_b200.so."""
+    """Compile every .cu under csrc/ (one nvcc per file, in parallel) and link them into
+    enspara_b200/libenspara_b200.so."""
     if not force and not needs_build():
         return LIB
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     env = dict(os.environ)
-    # the image's default host compiler (/opt/gcc) is fine for nvcc; keep PATH as is
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + sources()
-    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
-    log = res.stdout + res.stderr
+    objdir = os.path.join(CSRC, "build")
+    os.makedirs(objdir, exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        cmd = [nvcc] + compile_flags + ["-c", src, "-o", obj]
+        res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        return obj, " ".join(cmd) + "\n" + res.stdout + res.stderr, res.returncode
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, sources()))
+    log = "".join(r[1] for r in results)
+    ok = all(r[2] == 0 for r in results)
+    if ok:
+        cmd = [nvcc, "-shared", "-Xcompiler", "-fPIC", "-o", LIB] + [r[0] for r in results]
+        res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        log += " ".join(cmd) + "\n" + res.stdout + res.stderr
+        ok = res.returncode == 0
     with open(os.path.join(HERE, "csrc", "build.log"), "w") as fh:
-        fh.write(" ".join(cmd) + "\n" + log)
-    if res.returncode != 0:
+        fh.write(log)
+    if not ok:
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed building libenspara_b200.so")
     if verbose:
