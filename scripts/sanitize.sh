@@ -27,3 +27,19 @@ timeout 240 $CS --tool racecheck --print-limit 20 python -m pytest -q -x \
     "tests/test_gpu_tc_screen.py::test_tc_assign_equals_exact_assign" \
     > "$OUT/sanitize_racecheck_tc.log" 2>&1
 echo "racecheck tc rc=$? : $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' "$OUT/sanitize_racecheck_tc.log" | tail -1)"
+# round-2 additions: the persistent multi-iteration kernels (grid barrier, dynamic tail, TMA ring
+# across iterations), the compact pruned pass of PAM, the re-score bucketing, the xtc-free CLI
+for tool in memcheck racecheck; do
+  timeout 400 $CS --tool $tool --print-limit 20 python -m pytest -q -x \
+      "tests/test_gpu_features.py::test_multi_and_single_launches_mix" \
+      "tests/test_gpu_features.py::test_multi_iteration_kernel_edge_cases" \
+      "tests/test_gpu_kcenters_rmsd.py::test_persistent_multi_iteration_kernel_equals_single_launches[3001-50]" \
+      "tests/test_gpu_kmedoids.py::test_pam_pruned_full_pass_changes_nothing" \
+      "tests/test_gpu_tc_screen.py::test_tc_audit_every_call_and_detects_corruption" \
+      > "$OUT/sanitize_${tool}_round2.log" 2>&1
+  echo "$tool round2 rc=$? : $(grep -E 'passed|failed' "$OUT/sanitize_${tool}_round2.log" | tail -1) $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' "$OUT/sanitize_${tool}_round2.log" | tail -1)"
+done
+timeout 400 $CS --tool memcheck --print-limit 20 python -m pytest -q -x \
+    "tests/test_gpu_tc_screen.py::test_tc_assign_matches_oracle_other_atom_counts" \
+    > "$OUT/sanitize_memcheck_bucketing.log" 2>&1
+echo "memcheck bucketing rc=$? : $(grep -E 'passed|failed' "$OUT/sanitize_memcheck_bucketing.log" | tail -1) $(grep -E 'ERROR SUMMARY' "$OUT/sanitize_memcheck_bucketing.log" | tail -1)"
