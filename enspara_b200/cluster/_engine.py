@@ -325,11 +325,16 @@ class KCentersEngine:
         self._ensure_center_list(capacity)
         self._queued = n_existing
         queued = n_existing          # centre ids for which a launch has been queued
+        poll = self.POLL_EVERY
         while True:
             if bounded and cutoff <= 0.0:
                 batch = limit - queued
             else:
-                batch = min(self.POLL_EVERY, limit - queued)
+                # polls get rarer as the run gets longer (32, 64, 128, 128, ...): fewer state
+                # reads, and batches of >= 64 launches tell the library that this is a long,
+                # power-capped run (it then picks the kernel form that is faster sustained)
+                batch = min(poll, limit - queued)
+                poll = min(2 * poll, 4 * self.POLL_EVERY)
             if queued + batch > self.center_list.numel():
                 self._ensure_center_list(min(hard_cap, max(2 * self.center_list.numel(),
                                                            queued + batch)))

@@ -1190,7 +1190,11 @@ static int step_rmsd_impl(const float *xyz_soa, const double *traces, int64_t n,
     const int parts128 = A_pad_ / 128;
     const bool fr2_ok = use_tma && A_pad_ % 128 == 0 && parts128 >= 2 && parts128 <= 4 &&
                         step_tma_smem_bytes(A_pad_, parts128, 2, 2) <= 227 * 1024;
-    if (fr2_ok && (fr_env == 2 || (fr_env == 0 && parts128 <= 3))) {
+    // ... in a BURST.  A long run is power-capped (the step draws > 1000 W at full clocks:
+    // sw_power_cap, SM clock ~1.5 GHz) and then the form that moves fewer bytes through shared
+    // memory wins also at 512 floats: 600 iterations at 1.25M x 500, 1.282 -> 1.249 ms per
+    // iteration.  A batch of >= 64 queued iterations is taken as the sign of a long run.
+    if (fr2_ok && (fr_env == 2 || (fr_env == 0 && (parts128 <= 3 || n_steps >= 64)))) {
         FR = 2;
         P = A_pad_ / 128;
         S = 2;
