@@ -58,7 +58,8 @@ def build(force=False, verbose=False):
     log = "".join(r[1] for r in results)
     ok = all(r[2] == 0 for r in results)
     if ok:
-        cmd = [nvcc, "-shared", "-Xcompiler", "-fPIC", "-o", LIB] + [r[0] for r in results]
+        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler",
+               "-fPIC", "-o", LIB] + [r[0] for r in results]
         res = subprocess.run(cmd, capture_output=True, text=True, env=env)
         log += " ".join(cmd) + "\n" + res.stdout + res.stderr
         ok = res.returncode == 0
