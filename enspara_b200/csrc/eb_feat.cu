@@ -130,15 +130,51 @@ __device__ __forceinline__ double warp_rows_distance(const T *__restrict__ X, lo
 // being walked.
 // ------------------------------------------------------------------------------------------
 constexpr int kBoxBytes = 32 * 128;           // one box: 32 rows x 128 bytes
+constexpr int kMultiMaxThreads = 384;         // multi-iteration kernel: up to 12 warps per block
+constexpr int kKeepMB = 64;                   // L2-resident part of the shard (multi-iteration kernel)
 constexpr int kTmaTileBytes = 2 * kBoxBytes;  // 256 bytes of each of 32 rows
+
+// A full tile (256 bytes of each of the 32 rows), straight-line: row l of a box starts at
+// l * 128 and its 16-byte chunk c sits at ((c ^ (l & 7)) << 4); with the 128-byte aligned row
+// base that is ONE xor per load instead of the shift/mask/add sequence of the general loop
+// (the body was issue-bound, not HBM-bound: DESIGN.md K2).  Same terms, same order.
+template <typename T, int METRIC>
+__device__ __forceinline__ double tile_terms_full(double acc, const unsigned char *tile, int lane,
+                                                  const T *y_sh, long j0)
+{
+    constexpr int VE = 16 / (int)sizeof(T);
+    const uint32_t base = smem_u32(tile) + (uint32_t)lane * 128u + (uint32_t)((lane & 7) << 4);
+    const int4 *yq = reinterpret_cast<const int4 *>(y_sh + j0);
+#pragma unroll
+    for (int q = 0; q < kTileBytes / 16; ++q) {
+        int4 raw;
+        const uint32_t addr = (base ^ (uint32_t)((q & 7) << 4)) + (uint32_t)((q >> 3) * kBoxBytes);
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w)
+                     : "r"(addr)
+                     : "memory");
+        const int4 yraw = yq[q];    // broadcast read
+        const T *v = reinterpret_cast<const T *>(&raw);
+        const T *yv = reinterpret_cast<const T *>(&yraw);
+#pragma unroll
+        for (int u = 0; u < VE; ++u) acc = __dadd_rn(acc, Term<T, METRIC>::f(v[u], yv[u]));
+    }
+    return acc;
+}
 
 template <typename T, int METRIC>
 __device__ __forceinline__ double tile_terms_swz(double acc, const unsigned char *tile, int lane,
                                                  const T *y_sh, long j0, int fe)
 {
     constexpr int VE = 16 / (int)sizeof(T);
+#ifndef EB_K2_DIAG_SPLIT
+    if (fe == kTileBytes / (int)sizeof(T)) return tile_terms_full<T, METRIC>(acc, tile, lane, y_sh, j0);
+#endif
     const unsigned char *row = tile + lane * 128;
     const int sw = lane & 7;
+#ifdef EB_K2_DIAG_SPLIT
+    double acc2 = 0.0;
+#endif
 #pragma unroll 4
     for (int c = 0; c < fe; c += VE) {
         const int byteoff = c * (int)sizeof(T);
@@ -148,9 +184,20 @@ __device__ __forceinline__ double tile_terms_swz(double acc, const unsigned char
         const int4 yraw = *reinterpret_cast<const int4 *>(y_sh + j0 + c);  // broadcast read
         const T *v = reinterpret_cast<const T *>(&raw);
         const T *yv = reinterpret_cast<const T *>(&yraw);
+#ifdef EB_K2_DIAG_SPLIT   // diagnostic only (breaks the summation order): two chains per row
+#pragma unroll
+        for (int u = 0; u < VE; u += 2) {
+            acc = __dadd_rn(acc, Term<T, METRIC>::f(v[u], yv[u]));
+            acc2 = __dadd_rn(acc2, Term<T, METRIC>::f(v[u + 1], yv[u + 1]));
+        }
+#else
 #pragma unroll
         for (int u = 0; u < VE; ++u) acc = __dadd_rn(acc, Term<T, METRIC>::f(v[u], yv[u]));
+#endif
     }
+#ifdef EB_K2_DIAG_SPLIT
+    acc = __dadd_rn(acc, acc2);
+#endif
     return acc;
 }
 
@@ -246,7 +293,9 @@ k_kcenters_step_feat(const T *__restrict__ X, long n, long F, long frame_offset,
     unsigned char *tile = tiles + (size_t)warp * 2 * kTmaTileBytes;
 
     // commit one finished row (strict '<' update, arg-max tracking)
-    auto commit = [&](long row, double d) {
+    // `old` = the row's current distance; the pipelined path requests it before it waits for
+    // the row's first tile so that its latency hides behind the row sum
+    auto commit = [&](long row, double d, double old) {
         if (row < n) {
             double cur;
             if (MODE == kFSeed) {
@@ -255,7 +304,6 @@ k_kcenters_step_feat(const T *__restrict__ X, long n, long F, long frame_offset,
                 out_only[row] = d;
                 cur = 0.0;
             } else {
-                const double old = dist[row];
                 if (d < old) {  // strict '<', kcenters.py:304
                     dist[row] = d;
                     assign[row] = k;
@@ -297,18 +345,20 @@ k_kcenters_step_feat(const T *__restrict__ X, long n, long F, long frame_offset,
             }
         };
         uint32_t phase0 = 0, phase1 = 0;
-        double acc = 0.0;
+        double acc = 0.0, old_pre = 0.0;
         int c_buf = 0;
         if (p_chunk < n_chunks) issue();
         while (c_chunk < n_chunks) {
             if (p_chunk < n_chunks) issue();
+            if (MODE == kFStep && c_jt == 0 && (c_chunk << 5) + lane < n)
+                old_pre = dist[(c_chunk << 5) + lane];
             mbar_wait(bar + c_buf, c_buf ? phase1 : phase0);
             if (c_buf) phase1 ^= 1; else phase0 ^= 1;
             const long j0 = (long)c_jt * EPT;
             const int fe = (int)min((long)EPT, F - j0);
             acc = tile_terms_swz<T, METRIC>(acc, tile + c_buf * kTmaTileBytes, lane, y_sh, j0, fe);
             if (c_jt == nt - 1) {
-                commit((c_chunk << 5) + lane, finish<METRIC>(acc));
+                commit((c_chunk << 5) + lane, finish<METRIC>(acc), old_pre);
                 acc = 0.0;
             }
             c_buf ^= 1;
@@ -324,7 +374,7 @@ k_kcenters_step_feat(const T *__restrict__ X, long n, long F, long frame_offset,
             double d = 0.0;
             if (MODE != kFSeed)
                 d = warp_rows_distance<T, METRIC>(X, n, F, base, y_sh, tile, false);
-            commit(base + lane, d);
+            commit(base + lane, d, (MODE == kFStep && base + lane < n) ? dist[base + lane] : 0.0);
         }
     }
     if (MODE == kFDistOnly) return;
@@ -382,19 +432,21 @@ __device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned 
 }
 
 template <typename T, int METRIC>
-__global__ void __launch_bounds__(kFeatThreads)
+__global__ void __launch_bounds__(kMultiMaxThreads)
 k_kcenters_multi_feat(const T *__restrict__ X, long n, long F, long frame_offset,
                       unsigned char *cand, size_t rec_bytes, double *dist, int *assign,
                       int n_clusters_limit, double cutoff, eb_kc_state *state,
                       int64_t *center_list, Partial *partials, unsigned long long *gbar,
-                      int n_steps, const __grid_constant__ CUtensorMap tmap, unsigned int *dyn)
+                      int n_steps, const __grid_constant__ CUtensorMap tmap, unsigned int *dyn,
+                      long keep_chunks)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *tiles = smem_raw;
-    FeatSmem *ss = reinterpret_cast<FeatSmem *>(tiles + (size_t)kFeatWarps * 2 * kTmaTileBytes);
+    const int W = (int)(blockDim.x >> 5);      // warps per block: 12, 8 or 4 (launcher)
+    FeatSmem *ss = reinterpret_cast<FeatSmem *>(tiles + (size_t)W * 2 * kTmaTileBytes);
     uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(ss) +
                                                   align16(sizeof(FeatSmem)));
-    T *y_sh = reinterpret_cast<T *>(bars + 2 * kFeatWarps);
+    T *y_sh = reinterpret_cast<T *>(bars + 2 * W);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned G = gridDim.x;
@@ -415,8 +467,8 @@ k_kcenters_multi_feat(const T *__restrict__ X, long n, long F, long frame_offset
     constexpr int EPB = 128 / (int)sizeof(T);
     const int nt = (int)((F + EPT - 1) / EPT);
     const long n_chunks = (n + 31) >> 5;
-    const long warps_total = (long)G * kFeatWarps;
-    const long first_chunk = (long)blockIdx.x * kFeatWarps + warp;
+    const long warps_total = (long)G * W;
+    const long first_chunk = (long)blockIdx.x * W + warp;
     const bool has_work = first_chunk < n_chunks;
     unsigned char *tile = tiles + (size_t)warp * 2 * kTmaTileBytes;
     uint64_t *bar = bars + 2 * warp;
@@ -436,8 +488,8 @@ k_kcenters_multi_feat(const T *__restrict__ X, long n, long F, long frame_offset
     long p_slot = 0;                    // static chunks already issued in iteration p_iter
     long p_chunk = first_chunk;         // chunk being issued (valid while p_iter < n_steps)
     long ticket = -1;                   // prefetched dynamic ticket (-1: none)
-    long buf_chunk[2] = {0, 0};
-    int buf_iter[2] = {-1, -1};
+    long buf_chunk0 = 0, buf_chunk1 = 0;     // scalars, not arrays: dynamic indexing would put
+    int buf_iter0 = -1, buf_iter1 = -1;      // them in local memory, on the consumer's path
     auto fetch_ticket = [&](int iter) {
         unsigned int t = 0;
         if (lane == 0) t = atomicAdd(&dyn[iter & 1], 1u);
@@ -468,6 +520,7 @@ k_kcenters_multi_feat(const T *__restrict__ X, long n, long F, long frame_offset
             ++p_iter;
         }
     };
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
     auto try_issue = [&]() {
         if (!has_work || p_iter >= n_steps || inflight >= 2) return;
         if (lane == 0) {
@@ -476,12 +529,20 @@ k_kcenters_multi_feat(const T *__restrict__ X, long n, long F, long frame_offset
             const int n_box = (fe + EPB - 1) / EPB;
             unsigned char *dst = tile + p_buf * kTmaTileBytes;
             mbar_expect_tx(bar + p_buf, (uint32_t)n_box * kBoxBytes);
+            // the first keep_chunks chunks of the shard stay in L2 from one iteration to the
+            // next (evict_last); the rest streams through (evict_first)
+            const uint64_t pol = p_chunk < keep_chunks ? pol_keep : pol_stream;
             for (int b = 0; b < n_box; ++b)
-                tma_load_2d(dst + b * kBoxBytes, &tmap, (int)(j0 + (long)b * EPB),
-                            (int)(p_chunk << 5), bar + p_buf);
+                tma_load_2d_hint(dst + b * kBoxBytes, &tmap, (int)(j0 + (long)b * EPB),
+                                 (int)(p_chunk << 5), bar + p_buf, pol);
         }
-        buf_chunk[p_buf] = p_chunk;
-        buf_iter[p_buf] = p_iter;
+        if (p_buf) {
+            buf_chunk1 = p_chunk;
+            buf_iter1 = p_iter;
+        } else {
+            buf_chunk0 = p_chunk;
+            buf_iter0 = p_iter;
+        }
         p_buf ^= 1;
         ++inflight;
         if (++p_jt == nt) {
@@ -554,27 +615,30 @@ k_kcenters_multi_feat(const T *__restrict__ X, long n, long F, long frame_offset
         // ---- body: every row once, strict '<' update, arg-max --------------------------------
         double best_d = -2.0;
         int64_t best_i = INT64_MAX;
-        double acc = 0.0;
+        double acc = 0.0, old_pre = 0.0;
         if (dynamic_tail && blockIdx.x == 0 && threadIdx.x == 0) dyn[(it + 1) & 1] = 0u;
         int c_jt = 0;
         for (;;) {
             try_issue();
             // this iteration is over for the warp when the next tile in the ring belongs to
             // the following iteration, or nothing is left to request
-            if (inflight == 0 || buf_iter[c_buf] != it) break;
+            if (inflight == 0 || (c_buf ? buf_iter1 : buf_iter0) != it) break;
+            const long c_chunk = c_buf ? buf_chunk1 : buf_chunk0;
+            const long row = (c_chunk << 5) + lane;
+            // the row's current distance is requested before the tile is waited for, so its
+            // latency hides behind the row sum.  L2 read: a dynamically assigned chunk may have
+            // been updated by another SM in the previous iteration (L1 is not coherent across
+            // SMs); the grid barrier ordered that write before this read.
+            if (c_jt == 0 && row < n) old_pre = __ldcg(dist + row);
             wait_tile();
-            const long c_chunk = buf_chunk[c_buf];
             const long j0 = (long)c_jt * EPT;
             const int fe = (int)min((long)EPT, F - j0);
             acc = tile_terms_swz<T, METRIC>(acc, tile + c_buf * kTmaTileBytes, lane, y_sh, j0,
                                             fe);
             if (c_jt == nt - 1) {
-                const long row = (c_chunk << 5) + lane;
                 if (row < n) {
                     const double d = finish<METRIC>(acc);
-                    // L2 reads: a dynamically assigned chunk may have been updated by another
-                    // SM in the previous iteration (L1 is not coherent across SMs)
-                    const double old = __ldcg(dist + row);
+                    const double old = old_pre;
                     if (d < old) {  // strict '<', kcenters.py:304
                         dist[row] = d;
                         assign[row] = k;
@@ -783,6 +847,14 @@ static size_t elem_size(int dtype)
     return 0;
 }
 
+// the multi-iteration kernel: one block of up to 12 warps per SM (148 partials and pollers at
+// the arg-max barrier instead of 444)
+static size_t feat_multi_smem(long F, size_t es, int warps)
+{
+    return (size_t)warps * 2 * kTmaTileBytes + align16(sizeof(FeatSmem)) + 16 * warps +
+           align16((size_t)F * es) + 1024;
+}
+
 static size_t feat_smem(long F, size_t es, int n_y)
 {
     return (size_t)kFeatWarps * 2 * kTmaTileBytes + align16(sizeof(FeatSmem)) +
@@ -854,8 +926,11 @@ static int launch_feat_multi(const void *X, long n, long F, long frame_offset, v
                              int n_steps, cudaStream_t stream, int *used)
 {
     *used = 0;
-    const size_t smem = feat_smem(F, sizeof(T), 1);
+    int warps = 12;
+    while (warps > 4 && feat_multi_smem(F, sizeof(T), warps) > 227 * 1024) warps -= 4;
+    const size_t smem = feat_multi_smem(F, sizeof(T), warps);
     if (smem > 227 * 1024) return EB_OK;
+    const int threads = 32 * warps;
     const bool vec_ok = (((size_t)F * sizeof(T)) % 16 == 0) && (((uintptr_t)X) % 16 == 0) &&
                         n > 0 && n < (1L << 31) && F < (1L << 31) &&
                         (size_t)min((long)(128 / sizeof(T)), F) * sizeof(T) == 128;
@@ -876,11 +951,13 @@ static int launch_feat_multi(const void *X, long n, long F, long frame_offset, v
         configured = 227 * 1024;
     }
     int per_sm = 0;
-    EB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFeatThreads, smem));
+    EB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) return EB_OK;
-    int grid = feat_grid(n, smem);
+    const long chunks = (n + 31) / 32;
+    long grid_l = (chunks + warps - 1) / warps;
     const long cap = (long)per_sm * sm_count();
-    if (grid > cap) grid = (int)cap;
+    if (grid_l > cap) grid_l = cap;
+    int grid = (int)grid_l;
     if (2 * grid + 1 > kMaxGrid) return EB_OK;   // two partial buffers of `grid` entries + tickets
     CUtensorMap tmap;
     const int rc = make_tmap_2d(&tmap, X, tmap_dtype<T>(), sizeof(T), (uint64_t)n, (uint64_t)F,
@@ -895,9 +972,18 @@ static int launch_feat_multi(const void *X, long n, long F, long frame_offset, v
     // two ticket counters of the dynamic tail live behind the two partial buffers
     unsigned int *dyn = reinterpret_cast<unsigned int *>(pp + 2 * (size_t)grid);
     EB_CUDA(cudaMemsetAsync(dyn, 0, 2 * sizeof(unsigned int), stream));
+    // rows kept L2-resident across iterations (EB_K2_L2_MB, default kKeepMB); nothing is pinned
+    // when the whole shard fits anyway
+    static const long keep_mb = [] {
+        const char *e = getenv("EB_K2_L2_MB");
+        return e ? atol(e) : (long)kKeepMB;
+    }();
+    const size_t chunk_bytes = (size_t)32 * (size_t)F * sizeof(T);
+    long keep_chunks = (long)(((size_t)keep_mb << 20) / chunk_bytes);
     void *args[] = {&Xp, &n, &F, &frame_offset, &candp, &rec_bytes, &dist, &assign, &limit,
-                    &cutoff, &state, &center_list, &pp, &gbar, &n_steps, &tmap, &dyn};
-    EB_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(kFeatThreads), args,
+                    &cutoff, &state, &center_list, &pp, &gbar, &n_steps, &tmap, &dyn,
+                    &keep_chunks};
+    EB_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(threads), args,
                                         smem, stream));
     *used = 1;
     return EB_OK;

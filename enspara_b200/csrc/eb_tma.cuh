@@ -114,6 +114,30 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tmap, 
         "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// the same with an L2 eviction policy (createpolicy): rows a persistent kernel re-reads every
+// iteration are loaded evict_last, the streamed remainder evict_first, so the re-read part stays
+// L2-resident across iterations
+__device__ __forceinline__ void tma_load_2d_hint(void *dst, const CUtensorMap *tmap, int c0,
+                                                 int c1, uint64_t *bar, uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        ".L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+        "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tmap)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
