@@ -27,6 +27,30 @@ class KcState(ctypes.Structure):
 
 assert ctypes.sizeof(KcState) == 64
 
+
+class PamCtx(ctypes.Structure):
+    """Mirror of ``eb_pam_ctx`` (include/enspara_b200.h): the buffers of one PAM engine."""
+    _fields_ = [("xyz", ctypes.c_void_p), ("traces", ctypes.c_void_p), ("n", ctypes.c_int64),
+                ("frame_offset", ctypes.c_int64), ("n_atoms", ctypes.c_int32),
+                ("k", ctypes.c_int32), ("medoid_xyz", ctypes.c_void_p),
+                ("medoid_traces", ctypes.c_void_p), ("prop_xyz", ctypes.c_void_p),
+                ("prop_traces", ctypes.c_void_p), ("prop_idx", ctypes.c_void_p),
+                ("saved_xyz", ctypes.c_void_p), ("saved_traces", ctypes.c_void_p),
+                ("dist", ctypes.c_void_p), ("assign", ctypes.c_void_p),
+                ("new_dist", ctypes.c_void_p), ("new_assign", ctypes.c_void_p),
+                ("new_ctr_dist", ctypes.c_void_p), ("cc", ctypes.c_void_p),
+                ("need_idx", ctypes.c_void_p), ("need_n", ctypes.c_void_p),
+                ("need_assign", ctypes.c_void_p), ("ambig_idx", ctypes.c_void_p),
+                ("scal_i", ctypes.c_void_p), ("scal_d", ctypes.c_void_p),
+                ("scratch", ctypes.c_void_p), ("tc_cand", ctypes.c_void_p),
+                ("tc_scratch", ctypes.c_void_p), ("tc_ovf", ctypes.c_void_p),
+                ("kappa", ctypes.c_double), ("use_tc", ctypes.c_int32),
+                ("reserved", ctypes.c_int32), ("pin_d", ctypes.c_void_p),
+                ("pin_i", ctypes.c_void_p), ("pin_o", ctypes.c_void_p)]
+
+
+PAM_SELECT, PAM_TRIAL, PAM_READBACK = 1, 2, 4
+
 _vp, _i64, _i32, _int, _dbl, _sz, _u64 = (ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
                                            ctypes.c_int, ctypes.c_double, ctypes.c_size_t,
                                            ctypes.c_uint64)
@@ -83,6 +107,8 @@ SIGNATURES = {
     "eb_sum_squares": (_int, [_vp, _i64, _int, _vp, _vp, _vp]),
     "eb_count_members": (_int, [_vp, _i64, _i32, _vp, _vp]),
     "eb_select_member": (_int, [_vp, _i64, _i32, _i64, _vp, _vp, _vp]),
+    "eb_pam_propose_rmsd": (_int, [_vp, _i32, _i64, _i64, _int, _vp]),
+    "eb_pam_restore_medoid": (_int, [_vp, _i32, _vp]),
     "eb_xtc_scan": (_int, [ctypes.c_char_p, _vp, _vp]),
     "eb_xtc_read": (_int, [ctypes.c_char_p, _i64, _i64, _i64, _vp, _i32, _vp, _vp]),
     "eb_synth_trajectory_aos": (_int, [_vp, _i64, _int, _i64, _u64, _vp, _int, _vp]),

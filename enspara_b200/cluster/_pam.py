@@ -85,6 +85,16 @@ class PamEngine:
         self._pin_d = torch.zeros(1, dtype=torch.float64).pin_memory()
         self._pin_i = torch.zeros(2, dtype=torch.int64).pin_memory()
         self._pin_o = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.host_issue_s = 0.0
+        self.sync_wait_s = 0.0
+        self._t_proposal = time.perf_counter()
+        # RMSD with pruning: the whole proposal is queued by ONE C call (eb_pam_propose_rmsd);
+        # the per-step Python path below stays for feature metrics, profiling and the
+        # synchronous audited proposals
+        self._ctx = self._make_ctx() if (self.prune and self.prune_compact) else None
+        self._fast_ws = {"cap": 0}
+        self._red2 = torch.zeros(2, dtype=torch.float64, device=dev)
+        self._pin_d2 = torch.zeros(2, dtype=torch.float64).pin_memory()
 
     # -- helpers -------------------------------------------------------------------------
     def _to_dev(self, arr, dtype):
@@ -172,7 +182,12 @@ class PamEngine:
         self._pin_i.copy_(scal_i, non_blocking=True)
         if ovf is not None:
             self._pin_o.copy_(ovf, non_blocking=True)
+        t0 = time.perf_counter()
         torch.cuda.current_stream().synchronize()
+        t1 = time.perf_counter()
+        # diagnostic split of a proposal's wall time: host issuing work vs waiting for the GPU
+        self.host_issue_s += t0 - self._t_proposal
+        self.sync_wait_s += t1 - t0
         return (float(self._pin_d[0]), self._pin_i.clone(),
                 int(self._pin_o[0]) if ovf is not None else 0)
 
@@ -217,6 +232,144 @@ class PamEngine:
         if sh.size > 1:
             self.comm.broadcast(self.prop_buf, owner)
 
+    # -- one-call proposals (RMSD) ---------------------------------------------------------
+    def _make_ctx(self):
+        import ctypes
+        c = _lib.PamCtx()
+        d = self.data
+        c.xyz, c.traces, c.n, c.frame_offset = ptr(d.xyz), ptr(d.traces), self.n, self.shard.offset
+        c.n_atoms, c.k = d.n_atoms, self.k
+        c.medoid_xyz, c.medoid_traces = ptr(self.medoids.xyz), ptr(self.medoids.traces)
+        c.prop_xyz, c.prop_traces, c.prop_idx = (ptr(self.prop.xyz), ptr(self.prop.traces),
+                                                 ptr(self.prop_idx))
+        c.saved_xyz, c.saved_traces = ptr(self.saved.xyz), ptr(self.saved.traces)
+        c.new_ctr_dist, c.cc = ptr(self.new_ctr_dist), ptr(self.cc)
+        c.need_idx, c.need_n, c.need_assign = (ptr(self.need_idx), ptr(self.need_n),
+                                               ptr(self.need_assign))
+        c.ambig_idx, c.scal_i, c.scal_d = ptr(self.ambig_idx), ptr(self.scal_i), ptr(self.scal_d)
+        c.scratch = ptr(self.scratch)
+        c.kappa = float(_ops.tc_kappa(d.a_pad))
+        c.pin_d, c.pin_i, c.pin_o = (self._pin_d.data_ptr(), self._pin_i.data_ptr(),
+                                     self._pin_o.data_ptr())
+        self._ctx_ref = ctypes.byref(c)
+        self._ctx = c
+        self._ctx_state()
+        return c
+
+    def _ctx_state(self):
+        """Current / trial state pointers (they swap when a proposal is accepted)."""
+        c = self._ctx
+        c.dist, c.assign = ptr(self.dist), ptr(self.assign)
+        c.new_dist, c.new_assign = ptr(self.new_dist), ptr(self.new_assign)
+
+    def _ctx_workspace(self, m_max):
+        """Screen workspace of the one-call path, grown geometrically with the member count."""
+        ws = self._fast_ws
+        if ws.get("ovf") is None:
+            ws["ovf"] = torch.zeros(1, dtype=torch.int32, device=self.dev)
+            self._ctx.tc_ovf = ptr(ws["ovf"])
+        use_tc = bool(self.use_tc and m_max * self.k >= self.TC_MIN_PAIRS
+                      and 0 < m_max <= _ops.TC_CHUNK_FRAMES)
+        if use_tc and m_max > ws["cap"]:
+            cap = min(_ops.TC_CHUNK_FRAMES, m_max + m_max // 4 + 128)
+            need = int(self.lib.eb_tc_scratch_bytes(cap, self.data.n_atoms, self.k))
+            ws["scratch"] = ws["cand"] = None
+            ws["scratch"] = torch.empty(need, dtype=torch.uint8, device=self.dev)
+            ws["cand"] = torch.empty(cap, dtype=torch.int32, device=self.dev)
+            ws["cap"] = cap
+            self._ctx.tc_scratch, self._ctx.tc_cand = ptr(ws["scratch"]), ptr(ws["cand"])
+        self._ctx.use_tc = int(use_tc)
+        return use_tc
+
+    def _readback(self, with_ovf):
+        """The proposal's scalars with ONE stream synchronisation (sharded: after the cost's
+        all-reduce); the single-GPU one-call path has queued the copies already."""
+        sharded = self.shard.size > 1
+        if sharded:
+            # cost and overflow count travel in one all-reduce: every rank must take the same
+            # decision about the exact fallback (its cost is a collective again)
+            t = self._red2
+            t[0:1].copy_(self.scal_d)
+            t[1:2].copy_(self._fast_ws["ovf"])
+            self.comm.all_reduce_sum(t)
+            self._pin_d2.copy_(t, non_blocking=True)
+            self._pin_i.copy_(self.scal_i, non_blocking=True)
+        t0 = time.perf_counter()
+        torch.cuda.current_stream().synchronize()
+        t1 = time.perf_counter()
+        self.host_issue_s += t0 - self._t_proposal
+        self.sync_wait_s += t1 - t0
+        if sharded:
+            return float(self._pin_d2[0]), self._pin_i.clone(), int(self._pin_d2[1])
+        return (float(self._pin_d[0]), self._pin_i.clone(),
+                int(self._pin_o[0]) if with_ovf else 0)
+
+    def _draw_member(self, cid, rs, striped_randind):
+        """(owner rank, k-th member on the owner) of a random member of cluster cid, consuming
+        the reference's random stream (kmedoids.py:482-517, mpi/ops.py:247-268)."""
+        sh = self.shard
+        n_states = self._member_counts(cid)
+        total = int(n_states.sum())
+        if total < 1:
+            raise ValueError("'a' cannot be empty unless no samples are taken")
+        g = int(rs.randint(total))
+        if sh.size == 1:
+            return 0, g
+        if striped_randind:
+            concat = np.concatenate([np.arange(total)[r::sh.size] for r in range(sh.size)])
+            g = int(np.where(concat == g)[0][0])
+        bounds = np.concatenate([[0], np.cumsum(n_states)])
+        owner = int(np.searchsorted(bounds, g, side="right") - 1)
+        return owner, g - int(bounds[owner])
+
+    def _fast_proposal(self, cid, proposals, rs, striped_randind):
+        """One proposal through eb_pam_propose_rmsd.  Returns ((accepted, old_cost, new_cost,
+        accepted), proposal's global index) -- the tuple's tail is what the sweep logs."""
+        sh = self.shard
+        call, ctx, stream = _lib.call, self._ctx_ref, stream_ptr()
+        m_max = int(self._member_counts(cid)[sh.rank])
+        use_tc = self._ctx_workspace(m_max)
+        stages = _lib.PAM_TRIAL
+        kth = 0
+        if proposals is None:
+            owner, kth = self._draw_member(cid, rs, striped_randind)
+            prop_global = None
+            if sh.size == 1:
+                stages |= _lib.PAM_SELECT
+            else:
+                if sh.rank == owner:
+                    call("eb_pam_propose_rmsd", ctx, cid, kth, 0, _lib.PAM_SELECT, stream)
+                self.comm.broadcast(self.prop_buf, owner)
+        else:
+            prop_global = int(proposals[cid])
+            owner, loc = sh.to_rank_local(prop_global)
+            self._load_proposal(owner, local_idx=loc)
+        if sh.size == 1:
+            stages |= _lib.PAM_READBACK
+        call("eb_pam_propose_rmsd", ctx, cid, kth, m_max, stages, stream)
+        new_num, scal, n_ovf = self._readback(use_tc)
+        if n_ovf > 0:
+            # a candidate list overflowed: exact kernel for the subset, cost again
+            _ops.assign_device(self.metric, self.data, self.medoids, frame_idx=self.ambig_idx,
+                               n_idx=int(scal[1]), out_dist=self.new_dist,
+                               out_assign=self.new_assign, accumulate=False, scatter=True,
+                               k=self.k)
+            new_num = self._sumsq(self.new_dist)
+        if prop_global is None:
+            prop_global = int(scal[0])
+        old_cost = self.cost_num / self.n_global
+        new_cost = new_num / self.n_global
+        accepted = new_cost < old_cost
+        if accepted:
+            self.dist, self.new_dist = self.new_dist, self.dist
+            self.assign, self.new_assign = self.new_assign, self.assign
+            self._ctx_state()
+            self.cost_num = new_num
+            self.medoid_global[cid] = prop_global
+        else:
+            call("eb_pam_restore_medoid", ctx, cid, stream)
+        return (bool(accepted), old_cost, new_cost, bool(accepted)), prop_global
+
     # -- one sweep -----------------------------------------------------------------------
     def sweep(self, proposals=None, random_state=None, striped_randind=False, log=None,
               max_proposals=None):
@@ -252,6 +405,23 @@ class PamEngine:
         t = tick("counts", t)
         for cid in range(self.k if max_proposals is None else min(self.k, max_proposals)):
             # ---- proposal (kmedoids.py:616-628, 482-517) -------------------------------
+            self._t_proposal = time.perf_counter()
+            # Every TC_AUDIT_EVERY-th proposal (and any profiled one) takes the step-by-step
+            # path below, whose synchronous screen call also runs the audit; all others are
+            # queued by ONE C call and cost one stream synchronisation.
+            fast = (self._ctx is not None and prof is None and self.counts_by_rank is not None
+                    and ((self._proposals_done + 1) % _ops.TC_AUDIT_EVERY != 0
+                         or _ops._audit_level() == 0))
+            if fast:
+                accepted, prop_global = self._fast_proposal(cid, proposals, rs, striped_randind)
+                self._proposals_done += 1
+                if log is not None:
+                    log.append((cid, prop_global) + accepted[1:])
+                if accepted[0]:
+                    acceptances += 1
+                    if cid + 1 < self.k:
+                        self._refresh_counts()
+                continue
             if proposals is None:
                 n_states = self._member_counts(cid)
                 total = int(n_states.sum())
@@ -377,6 +547,8 @@ class PamEngine:
             if accepted:
                 self.dist, self.new_dist = self.new_dist, self.dist
                 self.assign, self.new_assign = self.new_assign, self.assign
+                if self._ctx is not None:
+                    self._ctx_state()
                 self.cost_num = new_num
                 self.medoid_global[cid] = prop_global
                 acceptances += 1

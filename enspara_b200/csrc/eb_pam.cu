@@ -231,6 +231,11 @@ __global__ void k_select_pick(const int *__restrict__ assign, long n, int cid, l
     if (lane == 0) *out = -1;
 }
 
+__global__ void k_global_index(const int64_t *local, int64_t offset, int64_t *out)
+{
+    out[0] = local[0] + offset;
+}
+
 static int pam_blocks(long n)
 {
     long b = (n + kPamThreads * 4 - 1) / (kPamThreads * 4);
@@ -344,6 +349,106 @@ int eb_select_member(const int32_t *assign, int64_t n, int32_t cid, int64_t kth,
     k_select_pick<<<1, 32, 0, s>>>(assign, n, cid, kth, per_block,
                                    (const unsigned long long *)scratch, nb, out);
     EB_LAUNCH_CHECK();
+    return EB_OK;
+}
+
+int eb_pam_propose_rmsd(const eb_pam_ctx *c, int32_t cid, int64_t kth, int64_t m_max, int stages,
+                        void *stream)
+{
+    EB_CHECK_ARG(c && c->xyz && c->traces && c->medoid_xyz && c->prop_xyz && c->scal_i &&
+                     c->scal_d && c->scratch,
+                 "pam_propose: missing buffers");
+    EB_CHECK_ARG(cid >= 0 && cid < c->k && c->k >= 2, "pam_propose: bad cluster id");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t frame_floats = 3 * (size_t)rmsd_apad(c->n_atoms);
+    int rc;
+    if (stages & EB_PAM_SELECT) {
+        rc = eb_select_member(c->assign, c->n, cid, kth, c->scal_i, c->scratch, stream);
+        if (rc != EB_OK) return rc;
+        rc = eb_gather_frames(c->xyz, c->traces, c->n_atoms, c->scal_i, 1, c->prop_xyz,
+                              c->prop_traces, stream);
+        if (rc != EB_OK) return rc;
+        k_global_index<<<1, 1, 0, s>>>(c->scal_i, c->frame_offset, c->prop_idx);
+        EB_LAUNCH_CHECK();
+    }
+    if (stages & EB_PAM_TRIAL) {
+        EB_CHECK_ARG(c->dist && c->assign && c->new_dist && c->new_assign && c->new_ctr_dist &&
+                         c->cc && c->need_idx && c->need_n && c->need_assign && c->ambig_idx &&
+                         c->saved_xyz,
+                     "pam_propose: missing buffers");
+        // distances proposal -> every medoid, then the pruned full pass (kmedoids.py:637)
+        rc = eb_rmsd_one_to_all(c->medoid_xyz, c->medoid_traces, c->k, c->n_atoms, c->prop_xyz,
+                                c->prop_traces, c->cc, 1, stream);
+        if (rc != EB_OK) return rc;
+        rc = eb_pam_need_list(c->dist, c->assign, c->cc, c->n, cid, c->new_ctr_dist, c->need_idx,
+                              c->need_n, stream);
+        if (rc != EB_OK) return rc;
+        if (c->n > 0) {
+            rc = eb_rmsd_assign_dev(c->xyz, c->traces, c->n, c->n_atoms, c->prop_xyz,
+                                    c->prop_traces, 1, c->need_idx, c->n, c->new_ctr_dist,
+                                    c->need_assign, 0, 1, (const int32_t *)c->need_n, stream);
+            if (rc != EB_OK) return rc;
+        }
+        // three-way split (kmedoids.py:644-658)
+        rc = eb_pam_classify(c->new_ctr_dist, c->dist, c->assign, c->n, 0, cid, c->new_dist,
+                             c->new_assign, c->ambig_idx, c->scal_i + 1, stream);
+        if (rc != EB_OK) return rc;
+        EB_CUDA(cudaMemcpyAsync(c->scal_i, c->prop_idx, sizeof(int64_t),
+                                cudaMemcpyDeviceToDevice, s));
+        // the proposal takes the medoid's slot (kmedoids.py:660-664); the old one is kept
+        float *slot = c->medoid_xyz + (size_t)cid * frame_floats;
+        EB_CUDA(cudaMemcpyAsync(c->saved_xyz, slot, frame_floats * sizeof(float),
+                                cudaMemcpyDeviceToDevice, s));
+        EB_CUDA(cudaMemcpyAsync(c->saved_traces, c->medoid_traces + cid, sizeof(double),
+                                cudaMemcpyDeviceToDevice, s));
+        EB_CUDA(cudaMemcpyAsync(slot, c->prop_xyz, frame_floats * sizeof(float),
+                                cudaMemcpyDeviceToDevice, s));
+        EB_CUDA(cudaMemcpyAsync(c->medoid_traces + cid, c->prop_traces, sizeof(double),
+                                cudaMemcpyDeviceToDevice, s));
+        // ambiguous frames against all medoids (kmedoids.py:666-670)
+        if (c->tc_ovf) EB_CUDA(cudaMemsetAsync(c->tc_ovf, 0, sizeof(int32_t), s));
+        if (m_max > 0) {
+            if (c->use_tc) {
+                EB_CHECK_ARG(c->tc_cand && c->tc_scratch && c->tc_ovf,
+                             "pam_propose: missing screen workspace");
+                rc = eb_rmsd_assign_tc_dev(c->xyz, c->traces, m_max, c->n_atoms, c->medoid_xyz,
+                                           c->medoid_traces, c->k, c->kappa, c->ambig_idx, 1,
+                                           c->new_dist, c->new_assign, c->tc_cand, c->tc_scratch,
+                                           nullptr, 1, (const int32_t *)(c->scal_i + 1),
+                                           c->tc_ovf, stream);
+            } else {
+                rc = eb_rmsd_assign_dev(c->xyz, c->traces, c->n, c->n_atoms, c->medoid_xyz,
+                                        c->medoid_traces, c->k, c->ambig_idx, m_max, c->new_dist,
+                                        c->new_assign, 0, 1, (const int32_t *)(c->scal_i + 1),
+                                        stream);
+            }
+            if (rc != EB_OK) return rc;
+        }
+        rc = eb_sum_squares(c->new_dist, c->n, 0, c->scal_d, c->scratch, stream);
+        if (rc != EB_OK) return rc;
+    }
+    if (stages & EB_PAM_READBACK) {
+        EB_CHECK_ARG(c->pin_d && c->pin_i, "pam_propose: missing pinned buffers");
+        EB_CUDA(cudaMemcpyAsync(c->pin_d, c->scal_d, sizeof(double), cudaMemcpyDeviceToHost, s));
+        EB_CUDA(cudaMemcpyAsync(c->pin_i, c->scal_i, 2 * sizeof(int64_t),
+                                cudaMemcpyDeviceToHost, s));
+        if (c->pin_o && c->tc_ovf)
+            EB_CUDA(cudaMemcpyAsync(c->pin_o, c->tc_ovf, sizeof(int32_t),
+                                    cudaMemcpyDeviceToHost, s));
+    }
+    return EB_OK;
+}
+
+int eb_pam_restore_medoid(const eb_pam_ctx *c, int32_t cid, void *stream)
+{
+    EB_CHECK_ARG(c && c->medoid_xyz && c->saved_xyz && cid >= 0 && cid < c->k,
+                 "pam_restore: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t frame_floats = 3 * (size_t)rmsd_apad(c->n_atoms);
+    EB_CUDA(cudaMemcpyAsync(c->medoid_xyz + (size_t)cid * frame_floats, c->saved_xyz,
+                            frame_floats * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    EB_CUDA(cudaMemcpyAsync(c->medoid_traces + cid, c->saved_traces, sizeof(double),
+                            cudaMemcpyDeviceToDevice, s));
     return EB_OK;
 }
 

@@ -622,6 +622,7 @@ k_rs_scatter(const unsigned char *__restrict__ key, long n, const int *__restric
 // cp.async.bulk into per-group double buffers (4 warps/SM, frame from L2) 14.1 ms.
 constexpr int RS_GROUPS = 16;            // frames per block
 constexpr int RS_THREADS = RS_GROUPS * 8;
+constexpr long RS_TEAM_MAX_FRAMES = 4096;  // at most this many frames: one block per frame (k_rescore_team)
 
 __global__ void __launch_bounds__(RS_THREADS, 5)
 k_rescore(const float *__restrict__ xyz, const double *__restrict__ traces, long n, int n_atoms,
@@ -746,6 +747,152 @@ k_rescore(const float *__restrict__ xyz, const double *__restrict__ traces, long
             }
         }
         __syncwarp();
+    }
+}
+
+
+// Re-score of a SMALL frame set (PAM's ambiguous subset: ~10^3 frames whose count lives on the
+// device): k_rescore gives every frame to one 8-lane group that walks the frame's survivors two
+// at a time, so its duration is the longest list (58 us per proposal at config 3, measured).
+// Here one BLOCK owns a frame: warp 0 merges the lists, the 16 groups take the survivors two at
+// a time in parallel, and the nearest (lowest index on ties) is reduced through shared memory.
+// Per pair the arithmetic is k_rescore's (same lanes, same atom order, same QCP), and the
+// minimum over (distance, index) does not depend on the order of evaluation, so the results are
+// identical.
+__global__ void __launch_bounds__(RS_THREADS, 5)
+k_rescore_team(const float *__restrict__ xyz, const double *__restrict__ traces, long n,
+               int n_atoms, int A_pad, const float *__restrict__ centers,
+               const double *__restrict__ ctraces, const int *__restrict__ cand_count,
+               const int *__restrict__ cand_list, const float *__restrict__ cand_bound,
+               const float *__restrict__ cand_umin, int n_seg, float *out_dist, int *out_assign,
+               int *frame_flag, const int64_t *__restrict__ frame_idx, int scatter, int MAX_CAND,
+               const int *__restrict__ f16_overflow, const int *__restrict__ n_dev,
+               int *ovf_count)
+{
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    __shared__ int sh_cnt, sh_ovf;
+    __shared__ float red_d[RS_GROUPS];
+    __shared__ int red_c[RS_GROUPS];
+    if (n_dev) n = min(n, (long)__ldg(n_dev));
+    int *cl = reinterpret_cast<int *>(rs_smem);                           // [n_seg * MAX_CAND]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, l8 = lane & 7;
+    const int grp = threadIdx.x >> 3;
+    const int A4 = A_pad >> 2;
+    const size_t stride = 3 * (size_t)A_pad;
+    for (long f = blockIdx.x; f < n; f += gridDim.x) {
+        // merge the frame's lists with every load independent of the others (a serial walk of
+        // 63 lists costs 63 dependent L2 round trips): global upper bound and overflow flag
+        // first, then every (list, slot) is tested by its own thread and the survivors are
+        // appended through a shared counter -- their order does not matter for the minimum
+        float U = INFINITY;
+        int ovf = 0;
+        for (int sgm = threadIdx.x; sgm < n_seg; sgm += RS_THREADS) {
+            U = fminf(U, cand_umin[(size_t)f * n_seg + sgm]);
+            ovf |= cand_count[(size_t)f * n_seg + sgm] < 0;
+        }
+#pragma unroll
+        for (int msk = 1; msk < 32; msk <<= 1) {
+            U = fminf(U, __shfl_xor_sync(0xffffffffu, U, msk));
+            ovf |= __shfl_xor_sync(0xffffffffu, ovf, msk);
+        }
+        if (lane == 0) {
+            red_d[warp] = U;
+            red_c[warp] = ovf;
+        }
+        if (threadIdx.x == 0) sh_cnt = 0;
+        __syncthreads();
+        U = fminf(fminf(red_d[0], red_d[1]), fminf(red_d[2], red_d[3]));
+        ovf = red_c[0] | red_c[1] | red_c[2] | red_c[3];
+        const bool overflow_all = ovf != 0 || __ldg(f16_overflow) != 0;
+        if (!overflow_all) {
+            const int slots = n_seg * MAX_CAND;
+            for (int sl = threadIdx.x; sl < slots; sl += RS_THREADS) {
+                const int sgm = sl / MAX_CAND, sidx = sl - sgm * MAX_CAND;
+                const int cnt = cand_count[(size_t)f * n_seg + sgm];
+                const size_t slot = ((size_t)f * n_seg + sgm) * MAX_CAND + sidx;
+                if (sidx < cnt && cand_bound[slot] <= U) cl[atomicAdd(&sh_cnt, 1)] = cand_list[slot];
+            }
+        }
+        if (threadIdx.x == 0) sh_ovf = overflow_all ? 1 : 0;
+        __syncthreads();
+        const int cnt_g = sh_cnt;
+        const bool overflow = sh_ovf != 0;
+        const long src = frame_idx ? (long)frame_idx[f] : f;
+        const float4 *px = reinterpret_cast<const float4 *>(xyz + (size_t)src * stride);
+        const double Ga = traces[src];
+        float best_d = INFINITY;
+        int best_c = 0x7fffffff;
+        // every group runs every trip (the shuffles below are warp-wide); idle ones skip the walk
+        for (int base = 0; base < cnt_g; base += 2 * RS_GROUPS) {
+            const int i0 = base + 2 * grp;
+            const bool act0 = i0 < cnt_g, act1 = i0 + 1 < cnt_g;
+            const int c0 = act0 ? cl[i0] : 0, c1 = act1 ? cl[i0 + 1] : c0;
+            const float4 *p0 = reinterpret_cast<const float4 *>(centers + (size_t)c0 * stride);
+            const float4 *p1 = reinterpret_cast<const float4 *>(centers + (size_t)c1 * stride);
+            double m0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, m1[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            if (act0) {
+#pragma unroll 2
+                for (int j = l8; j < A4; j += 8) {
+                    const float4 x = __ldg(px + j), y = __ldg(px + A4 + j),
+                                 z = __ldg(px + 2 * A4 + j);
+                    const float4 ax = __ldg(p0 + j), ay = __ldg(p0 + A4 + j),
+                                 az = __ldg(p0 + 2 * A4 + j);
+                    const float4 bx = __ldg(p1 + j), by = __ldg(p1 + A4 + j),
+                                 bz = __ldg(p1 + 2 * A4 + j);
+                    acc_atom(m0, x.x, y.x, z.x, (double)ax.x, (double)ay.x, (double)az.x);
+                    acc_atom(m0, x.y, y.y, z.y, (double)ax.y, (double)ay.y, (double)az.y);
+                    acc_atom(m0, x.z, y.z, z.z, (double)ax.z, (double)ay.z, (double)az.z);
+                    acc_atom(m0, x.w, y.w, z.w, (double)ax.w, (double)ay.w, (double)az.w);
+                    acc_atom(m1, x.x, y.x, z.x, (double)bx.x, (double)by.x, (double)bz.x);
+                    acc_atom(m1, x.y, y.y, z.y, (double)bx.y, (double)by.y, (double)bz.y);
+                    acc_atom(m1, x.z, y.z, z.z, (double)bx.z, (double)by.z, (double)bz.z);
+                    acc_atom(m1, x.w, y.w, z.w, (double)bx.w, (double)by.w, (double)bz.w);
+                }
+            }
+            group8_reduce(m0);
+            group8_reduce(m1);
+            if (act0) {
+                const float d = rmsd_from_msd(qcp_msd(m0, Ga, ctraces[c0], n_atoms));
+                if (d < best_d || (d == best_d && c0 < best_c)) {
+                    best_d = d;
+                    best_c = c0;
+                }
+            }
+            if (act1) {
+                const float d = rmsd_from_msd(qcp_msd(m1, Ga, ctraces[c1], n_atoms));
+                if (d < best_d || (d == best_d && c1 < best_c)) {
+                    best_d = d;
+                    best_c = c1;
+                }
+            }
+        }
+        if (l8 == 0) {
+            red_d[grp] = best_d;
+            red_c[grp] = best_c;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (overflow || cnt_g == 0) {
+                frame_flag[f] = -1;  // the host sends this frame through the exact kernel
+                if (ovf_count) atomicAdd(ovf_count, 1);
+            } else {
+                float bd = red_d[0];
+                int bc = red_c[0];
+                for (int g2 = 1; g2 < RS_GROUPS; ++g2) {
+                    const float d = red_d[g2];
+                    const int c = red_c[g2];
+                    if (d < bd || (d == bd && c < bc)) {
+                        bd = d;
+                        bc = c;
+                    }
+                }
+                frame_flag[f] = cnt_g;
+                const long o = scatter ? src : f;
+                out_dist[o] = bd;
+                out_assign[o] = bc;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -945,7 +1092,21 @@ int eb_rmsd_assign_tc_dev(const float *xyz_soa, const double *traces, int64_t n,
                                                  bins + 2 * tc::RS_BINS, order);
         EB_LAUNCH_CHECK();
     }
-    {
+    if (n <= tc::RS_TEAM_MAX_FRAMES) {
+        // small frame sets (PAM's ambiguous subset): one block per frame
+        const size_t rs_smem = align16(sizeof(int) * n_lists * max_cand);
+        long blocks = n < 5L * sm_count() ? n : 5L * sm_count();
+        if (blocks < 1) blocks = 1;
+        EB_CHECK_ARG(rs_smem <= 200 * 1024, "rmsd_assign_tc: candidate lists too large");
+        EB_CUDA(cudaFuncSetAttribute(tc::k_rescore_team,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(rs_smem > 48 * 1024 ? rs_smem : 48 * 1024)));
+        tc::k_rescore_team<<<(int)blocks, tc::RS_THREADS, rs_smem, s>>>(
+            xyz_soa, traces, n, n_atoms, A_pad, centers_soa, center_traces, seg_count, cand_list,
+            cand_bound, cand_umin, (int)n_lists, out_dist, out_assign, cand_count, frame_idx,
+            scatter, max_cand, f16_overflow, n_dev, overflow_count);
+        EB_LAUNCH_CHECK();
+    } else {
         const size_t rs_smem = align16(sizeof(int) * tc::RS_GROUPS * n_lists * max_cand);
         long blocks = (n + tc::RS_GROUPS - 1) / tc::RS_GROUPS;
         if (blocks > 10L * sm_count()) blocks = 10L * sm_count();

@@ -291,6 +291,66 @@ int eb_count_members(const int32_t *assign, int64_t n, int32_t k, int64_t *count
 int eb_select_member(const int32_t *assign, int64_t n, int32_t cid, int64_t kth, int64_t *out,
                      void *scratch, void *stream);
 
+/* One PAM proposal for an RMSD shard, queued with ONE call (the sequence the host layer
+ * otherwise issues as ~25 separate launches / copies; kmedoids.py:609-694 for one cluster id).
+ * All pointers are device memory owned by the caller except pin_*, which are pinned host
+ * memory.  `stages` is a bit mask:
+ *   EB_PAM_SELECT  the kth member of cluster cid (eb_select_member) is gathered into the
+ *                  proposal slot and prop_idx[0] = its GLOBAL index (the owner rank's part,
+ *                  kmedoids.py:482-517; a sharded run broadcasts the slot afterwards);
+ *   EB_PAM_TRIAL   cc = d(proposal, every medoid); triangle-inequality need list + exact
+ *                  distances proposal -> those frames; three-way split (eb_pam_classify);
+ *                  scal_i = {prop_idx, n_ambig}; medoid cid saved and replaced by the proposal;
+ *                  the ambiguous frames (at most m_max, real count on the device) re-assigned
+ *                  against all k medoids (tensor-core screen + exact re-score when use_tc, else
+ *                  the exact kernel); scal_d = sum(new_dist^2);
+ *   EB_PAM_READBACK scal_d, scal_i and tc_ovf copied to pin_d / pin_i / pin_o (asynchronous;
+ *                  the caller synchronises the stream once).
+ * eb_pam_restore_medoid puts the saved medoid back after a rejected proposal. */
+#define EB_PAM_SELECT 1
+#define EB_PAM_TRIAL 2
+#define EB_PAM_READBACK 4
+typedef struct eb_pam_ctx {
+    const float *xyz;            /* shard, SoA (n, 3, A_pad) */
+    const double *traces;
+    int64_t n;
+    int64_t frame_offset;        /* global index of local frame 0 */
+    int32_t n_atoms;
+    int32_t k;
+    float *medoid_xyz;           /* (k, 3, A_pad) */
+    double *medoid_traces;
+    float *prop_xyz;             /* proposal slot, one frame */
+    double *prop_traces;
+    int64_t *prop_idx;           /* its global index */
+    float *saved_xyz;            /* the medoid the proposal displaces */
+    double *saved_traces;
+    const float *dist;           /* current state */
+    const int32_t *assign;
+    float *new_dist;             /* trial state */
+    int32_t *new_assign;
+    float *new_ctr_dist;         /* (n) distances to the proposal, +inf where pruned */
+    float *cc;                   /* (k) */
+    int64_t *need_idx;           /* (n) */
+    int64_t *need_n;             /* (1) */
+    int32_t *need_assign;        /* (n) */
+    int64_t *ambig_idx;          /* (n) */
+    int64_t *scal_i;             /* (2) {proposal, n_ambig} */
+    double *scal_d;              /* (1) */
+    void *scratch;               /* eb_pam_scratch_bytes */
+    int32_t *tc_cand;            /* tensor-core screen workspace for m_max frames */
+    void *tc_scratch;
+    int32_t *tc_ovf;             /* (1) frames whose candidate lists overflowed */
+    double kappa;
+    int32_t use_tc;
+    int32_t reserved;
+    double *pin_d;               /* pinned host: (1), (2), (1) */
+    int64_t *pin_i;
+    int32_t *pin_o;
+} eb_pam_ctx;
+int eb_pam_propose_rmsd(const eb_pam_ctx *ctx, int32_t cid, int64_t kth, int64_t m_max,
+                        int stages, void *stream);
+int eb_pam_restore_medoid(const eb_pam_ctx *ctx, int32_t cid, void *stream);
+
 /* ---- trajectory input without mdtraj: native GROMACS .xtc reader (host code) -------------
  * Replaces md.load(path, stride=, atom_indices=) for .xtc files in the loaders either side of
  * the hot path (cluster/util.py:350-404 load_trajectories, mpi/io.py:142-194
