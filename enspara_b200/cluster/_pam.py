@@ -52,8 +52,12 @@ class PamEngine:
         self.new_ctr_dist = torch.empty_like(self.dist)
         self.ambig_idx = torch.empty(max(self.n, 1), dtype=torch.int64, device=dev)
         # scalars read back per proposal: [proposed local index, n_ambig] and [cost numerator]
-        self.scal_i = torch.zeros(2, dtype=torch.int64, device=dev)
-        self.scal_d = torch.zeros(1, dtype=torch.float64, device=dev)
+        # (one 32-byte block {cost f64, proposal i64, n_ambig i64, overflow i32} on the device
+        # and in pinned host memory, so the read-back is a single copy)
+        self._scal_all = torch.zeros(4, dtype=torch.int64, device=dev)
+        self.scal_d = self._scal_all[0:1].view(torch.float64)
+        self.scal_i = self._scal_all[1:3]
+        self._ovf = self._scal_all[3:4].view(torch.int32)[0:1]
         self.scratch = torch.empty(int(self.lib.eb_pam_scratch_bytes(self.n)),
                                    dtype=torch.uint8, device=dev)
         self.k = len(medoid_global_inds)
@@ -82,9 +86,10 @@ class PamEngine:
         self._proposals_done = 0
         # pinned landing zone of the one read-back per proposal: [cost], [proposal, n_ambig],
         # [overflowed frames]
-        self._pin_d = torch.zeros(1, dtype=torch.float64).pin_memory()
-        self._pin_i = torch.zeros(2, dtype=torch.int64).pin_memory()
-        self._pin_o = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._pin_all = torch.zeros(4, dtype=torch.int64).pin_memory()
+        self._pin_d = self._pin_all[0:1].view(torch.float64)
+        self._pin_i = self._pin_all[1:3]
+        self._pin_o = self._pin_all[3:4].view(torch.int32)[0:1]
         self.host_issue_s = 0.0
         self.sync_wait_s = 0.0
         self._t_proposal = time.perf_counter()
@@ -266,7 +271,7 @@ class PamEngine:
         """Screen workspace of the one-call path, grown geometrically with the member count."""
         ws = self._fast_ws
         if ws.get("ovf") is None:
-            ws["ovf"] = torch.zeros(1, dtype=torch.int32, device=self.dev)
+            ws["ovf"] = self._ovf
             self._ctx.tc_ovf = ptr(ws["ovf"])
         use_tc = bool(self.use_tc and m_max * self.k >= self.TC_MIN_PAIRS
                       and 0 < m_max <= _ops.TC_CHUNK_FRAMES)

@@ -171,64 +171,106 @@ k_select_count(const int *__restrict__ assign, long n, int cid, long per_block,
     if (threadIdx.x == 0) block_counts[blockIdx.x] = sh;
 }
 
-// pass 2 (one warp): find the block holding the kth member, then walk that block's range
-__global__ void k_select_pick(const int *__restrict__ assign, long n, int cid, long kth,
-                              long per_block, const unsigned long long *block_counts, int nb,
-                              int64_t *out)
+// pass 2 (one block): find the counting block holding the kth member, then the member in it
+__global__ void __launch_bounds__(1024)
+k_select_pick(const int32_t *__restrict__ assign, long n, int32_t cid, long kth, long per_block,
+              const unsigned long long *block_counts, int nb, int64_t *out)
 {
-    const int lane = threadIdx.x;
+    // One block of 1024 threads; every load of a phase is independent of the others (the first
+    // version walked 31 + 32 dependent 32-wide steps with one warp: 11 us per proposal).
+    __shared__ long s_warp[32];
     __shared__ long s_block, s_rem;
-    {
-        // warp-parallel scan of the block counts, 32 at a time (inclusive prefix by shuffles)
-        long rem = kth;
-        int found = nb;
-        for (int b0 = 0; b0 < nb && found == nb; b0 += 32) {
-            const int b = b0 + lane;
-            const long c = b < nb ? (long)block_counts[b] : 0;
-            long inc = c;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // ---- phase 1: which counting block holds the kth member ---------------------------------
+    const int cpt = (nb + 1023) / 1024;                  // block counts per thread
+    long own = 0;
+    for (int j = 0; j < cpt; ++j) {
+        const int b = tid * cpt + j;
+        if (b < nb) own += (long)block_counts[b];
+    }
+    long inc = own;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const long up = __shfl_up_sync(0xffffffffu, inc, d);
-                if (lane >= d) inc += up;
+    for (int d = 1; d < 32; d <<= 1) {
+        const long up = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += up;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    if (tid == 0) {
+        s_block = nb;
+        s_rem = 0;
+    }
+    __syncthreads();
+    long before = 0;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    const long ex = before + inc - own;                  // members in blocks before this thread's
+    if (kth >= ex && kth < ex + own) {                   // exactly one thread
+        long rem = kth - ex;
+        for (int j = 0; j < cpt; ++j) {
+            const int b = tid * cpt + j;
+            const long c = (long)block_counts[b];
+            if (rem < c) {
+                s_block = b;
+                s_rem = rem;
+                break;
             }
-            const unsigned hit = __ballot_sync(0xffffffffu, b < nb && rem < inc);
-            if (hit) {
-                const int l = __ffs(hit) - 1;          // first block whose prefix exceeds rem
-                const long before = __shfl_sync(0xffffffffu, inc - c, l);
-                found = b0 + l;
-                rem -= before;
-            } else {
-                rem -= __shfl_sync(0xffffffffu, inc, 31);
-            }
-        }
-        if (lane == 0) {
-            s_block = found;
-            s_rem = rem;
+            rem -= c;
         }
     }
-    __syncwarp();
+    __syncthreads();
     if (s_block >= nb) {
-        if (lane == 0) *out = -1;
+        if (tid == 0) *out = -1;
         return;
     }
+    // ---- phase 2: the (rem)-th member inside that block's range -----------------------------
     const long lo = s_block * per_block;
     const long hi = min(n, lo + per_block);
     long rem = s_rem;
-    for (long base = lo; base < hi; base += 32) {
-        const long i = base + lane;
+    for (long base = lo; base < hi; base += 1024) {
+        const long i = base + tid;
         const bool hit = (i < hi) && (assign[i] == cid);
         const unsigned mask = __ballot_sync(0xffffffffu, hit);
-        const int c = __popc(mask);
-        if (rem < c) {
-            // the (rem)-th set bit of mask
-            unsigned mm = mask;
-            for (long t = 0; t < rem; ++t) mm &= mm - 1;
-            if (lane == 0) *out = base + (__ffs(mm) - 1);
+        __syncthreads();                                  // s_warp free again
+        if (lane == 0) s_warp[warp] = __popc(mask);
+        __syncthreads();
+        long pre = 0, total = 0;
+        for (int w = 0; w < 32; ++w) {
+            const long c = s_warp[w];
+            if (w < warp) pre += c;
+            total += c;
+        }
+        if (rem < total) {
+            if (hit && pre + __popc(mask & ((1u << lane) - 1u)) == rem) *out = i;
             return;
         }
-        rem -= c;
+        rem -= total;
     }
-    if (lane == 0) *out = -1;
+    if (tid == 0) *out = -1;
+}
+
+// The proposal takes medoid cid's slot, the displaced medoid is kept for a rejection
+// (kmedoids.py:660-664); scal_i[0] = the proposal's global index; the screen's overflow counter
+// is cleared.  One launch instead of five small copies and a memset.
+__global__ void k_take_slot(float *slot, double *slot_trace, float *saved, double *saved_trace,
+                            const float *prop, const double *prop_trace, long frame_floats,
+                            int64_t *scal_i, const int64_t *prop_idx, int32_t *tc_ovf)
+{
+    for (long i = threadIdx.x; i < frame_floats; i += blockDim.x) {
+        saved[i] = slot[i];
+        slot[i] = prop[i];
+    }
+    if (threadIdx.x == 0) {
+        *saved_trace = *slot_trace;
+        *slot_trace = *prop_trace;
+        scal_i[0] = prop_idx[0];
+        if (tc_ovf) *tc_ovf = 0;
+    }
+}
+
+__global__ void k_restore_slot(float *slot, double *slot_trace, const float *saved,
+                               const double *saved_trace, long frame_floats)
+{
+    for (long i = threadIdx.x; i < frame_floats; i += blockDim.x) slot[i] = saved[i];
+    if (threadIdx.x == 0) *slot_trace = *saved_trace;
 }
 
 __global__ void k_global_index(const int64_t *local, int64_t offset, int64_t *out)
@@ -346,7 +388,7 @@ int eb_select_member(const int32_t *assign, int64_t n, int32_t cid, int64_t kth,
     k_select_count<<<nb, kPamThreads, 0, s>>>(assign, n, cid, per_block,
                                               (unsigned long long *)scratch);
     EB_LAUNCH_CHECK();
-    k_select_pick<<<1, 32, 0, s>>>(assign, n, cid, kth, per_block,
+    k_select_pick<<<1, 1024, 0, s>>>(assign, n, cid, kth, per_block,
                                    (const unsigned long long *)scratch, nb, out);
     EB_LAUNCH_CHECK();
     return EB_OK;
@@ -393,20 +435,13 @@ int eb_pam_propose_rmsd(const eb_pam_ctx *c, int32_t cid, int64_t kth, int64_t m
         rc = eb_pam_classify(c->new_ctr_dist, c->dist, c->assign, c->n, 0, cid, c->new_dist,
                              c->new_assign, c->ambig_idx, c->scal_i + 1, stream);
         if (rc != EB_OK) return rc;
-        EB_CUDA(cudaMemcpyAsync(c->scal_i, c->prop_idx, sizeof(int64_t),
-                                cudaMemcpyDeviceToDevice, s));
         // the proposal takes the medoid's slot (kmedoids.py:660-664); the old one is kept
-        float *slot = c->medoid_xyz + (size_t)cid * frame_floats;
-        EB_CUDA(cudaMemcpyAsync(c->saved_xyz, slot, frame_floats * sizeof(float),
-                                cudaMemcpyDeviceToDevice, s));
-        EB_CUDA(cudaMemcpyAsync(c->saved_traces, c->medoid_traces + cid, sizeof(double),
-                                cudaMemcpyDeviceToDevice, s));
-        EB_CUDA(cudaMemcpyAsync(slot, c->prop_xyz, frame_floats * sizeof(float),
-                                cudaMemcpyDeviceToDevice, s));
-        EB_CUDA(cudaMemcpyAsync(c->medoid_traces + cid, c->prop_traces, sizeof(double),
-                                cudaMemcpyDeviceToDevice, s));
+        k_take_slot<<<1, 512, 0, s>>>(c->medoid_xyz + (size_t)cid * frame_floats,
+                                      c->medoid_traces + cid, c->saved_xyz, c->saved_traces,
+                                      c->prop_xyz, c->prop_traces, (long)frame_floats, c->scal_i,
+                                      c->prop_idx, c->tc_ovf);
+        EB_LAUNCH_CHECK();
         // ambiguous frames against all medoids (kmedoids.py:666-670)
-        if (c->tc_ovf) EB_CUDA(cudaMemsetAsync(c->tc_ovf, 0, sizeof(int32_t), s));
         if (m_max > 0) {
             if (c->use_tc) {
                 EB_CHECK_ARG(c->tc_cand && c->tc_scratch && c->tc_ovf,
@@ -429,12 +464,23 @@ int eb_pam_propose_rmsd(const eb_pam_ctx *c, int32_t cid, int64_t kth, int64_t m
     }
     if (stages & EB_PAM_READBACK) {
         EB_CHECK_ARG(c->pin_d && c->pin_i, "pam_propose: missing pinned buffers");
-        EB_CUDA(cudaMemcpyAsync(c->pin_d, c->scal_d, sizeof(double), cudaMemcpyDeviceToHost, s));
-        EB_CUDA(cudaMemcpyAsync(c->pin_i, c->scal_i, 2 * sizeof(int64_t),
-                                cudaMemcpyDeviceToHost, s));
-        if (c->pin_o && c->tc_ovf)
-            EB_CUDA(cudaMemcpyAsync(c->pin_o, c->tc_ovf, sizeof(int32_t),
+        const bool packed = c->pin_o && c->tc_ovf &&
+                            (const char *)c->scal_i == (const char *)c->scal_d + 8 &&
+                            (const char *)c->tc_ovf == (const char *)c->scal_d + 24 &&
+                            (const char *)c->pin_i == (const char *)c->pin_d + 8 &&
+                            (const char *)c->pin_o == (const char *)c->pin_d + 24;
+        if (packed) {
+            // {cost, proposal, n_ambig, overflow} are adjacent on both sides: one copy
+            EB_CUDA(cudaMemcpyAsync(c->pin_d, c->scal_d, 32, cudaMemcpyDeviceToHost, s));
+        } else {
+            EB_CUDA(cudaMemcpyAsync(c->pin_d, c->scal_d, sizeof(double), cudaMemcpyDeviceToHost,
+                                    s));
+            EB_CUDA(cudaMemcpyAsync(c->pin_i, c->scal_i, 2 * sizeof(int64_t),
                                     cudaMemcpyDeviceToHost, s));
+            if (c->pin_o && c->tc_ovf)
+                EB_CUDA(cudaMemcpyAsync(c->pin_o, c->tc_ovf, sizeof(int32_t),
+                                        cudaMemcpyDeviceToHost, s));
+        }
     }
     return EB_OK;
 }
@@ -445,10 +491,10 @@ int eb_pam_restore_medoid(const eb_pam_ctx *c, int32_t cid, void *stream)
                  "pam_restore: bad arguments");
     cudaStream_t s = (cudaStream_t)stream;
     const size_t frame_floats = 3 * (size_t)rmsd_apad(c->n_atoms);
-    EB_CUDA(cudaMemcpyAsync(c->medoid_xyz + (size_t)cid * frame_floats, c->saved_xyz,
-                            frame_floats * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    EB_CUDA(cudaMemcpyAsync(c->medoid_traces + cid, c->saved_traces, sizeof(double),
-                            cudaMemcpyDeviceToDevice, s));
+    k_restore_slot<<<1, 512, 0, s>>>(c->medoid_xyz + (size_t)cid * frame_floats,
+                                     c->medoid_traces + cid, c->saved_xyz, c->saved_traces,
+                                     (long)frame_floats);
+    EB_LAUNCH_CHECK();
     return EB_OK;
 }
 
