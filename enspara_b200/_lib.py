@@ -46,7 +46,9 @@ class PamCtx(ctypes.Structure):
                 ("tc_scratch", ctypes.c_void_p), ("tc_ovf", ctypes.c_void_p),
                 ("kappa", ctypes.c_double), ("use_tc", ctypes.c_int32),
                 ("reserved", ctypes.c_int32), ("pin_d", ctypes.c_void_p),
-                ("pin_i", ctypes.c_void_p), ("pin_o", ctypes.c_void_p)]
+                ("pin_i", ctypes.c_void_p), ("pin_o", ctypes.c_void_p),
+                ("med_list", ctypes.c_void_p), ("med_list_n", ctypes.c_void_p),
+                ("med_list_cap", ctypes.c_int32), ("use_list", ctypes.c_int32)]
 
 
 PAM_SELECT, PAM_TRIAL, PAM_READBACK = 1, 2, 4
@@ -109,6 +111,7 @@ SIGNATURES = {
     "eb_select_member": (_int, [_vp, _i64, _i32, _i64, _vp, _vp, _vp]),
     "eb_pam_propose_rmsd": (_int, [_vp, _i32, _i64, _i64, _int, _vp]),
     "eb_pam_restore_medoid": (_int, [_vp, _i32, _vp]),
+    "eb_struct_bytes": (_sz, [_int]),
     "eb_xtc_scan": (_int, [ctypes.c_char_p, _vp, _vp]),
     "eb_xtc_read": (_int, [ctypes.c_char_p, _i64, _i64, _i64, _vp, _i32, _vp, _vp]),
     "eb_synth_trajectory_aos": (_int, [_vp, _i64, _int, _i64, _u64, _vp, _int, _vp]),

@@ -256,6 +256,15 @@ class PamEngine:
         c.kappa = float(_ops.tc_kappa(d.a_pad))
         c.pin_d, c.pin_i, c.pin_o = (self._pin_d.data_ptr(), self._pin_i.data_ptr(),
                                      self._pin_o.data_ptr())
+        # medoids the triangle inequality leaves for the ambiguous frames (PAM):
+        # ENSPARA_B200_PAM_LIST=0 keeps the all-medoids re-assignment
+        import os
+        cap = min(self.k, 1024)
+        self._med_list = torch.zeros(cap + 2, dtype=torch.int32, device=self.dev)
+        c.med_list, c.med_list_n, c.med_list_cap = (ptr(self._med_list[2:]),
+                                                    ptr(self._med_list[:1]), cap)
+        c.use_list = int(os.environ.get("ENSPARA_B200_PAM_LIST", "1") != "0")
+        self._list_overflows = 0
         self._ctx_ref = ctypes.byref(c)
         self._ctx = c
         self._ctx_state()
@@ -273,6 +282,8 @@ class PamEngine:
         if ws.get("ovf") is None:
             ws["ovf"] = self._ovf
             self._ctx.tc_ovf = ptr(ws["ovf"])
+        if self._ctx.use_list:
+            return True                  # overflow counter: more listed medoids than the cap
         use_tc = bool(self.use_tc and m_max * self.k >= self.TC_MIN_PAIRS
                       and 0 < m_max <= _ops.TC_CHUNK_FRAMES)
         if use_tc and m_max > ws["cap"]:
@@ -354,12 +365,25 @@ class PamEngine:
         call("eb_pam_propose_rmsd", ctx, cid, kth, m_max, stages, stream)
         new_num, scal, n_ovf = self._readback(use_tc)
         if n_ovf > 0:
-            # a candidate list overflowed: exact kernel for the subset, cost again
-            _ops.assign_device(self.metric, self.data, self.medoids, frame_idx=self.ambig_idx,
-                               n_idx=int(scal[1]), out_dist=self.new_dist,
-                               out_assign=self.new_assign, accumulate=False, scatter=True,
-                               k=self.k)
+            # a candidate list (screen) or the medoid list overflowed somewhere: the subset
+            # goes through the general path on every rank, and the cost is taken again
+            n_ambig = int(scal[1])
+            if n_ambig > 0 and self.use_tc:
+                _ops.assign_device_tc(self.metric, self.data, self.medoids, k=self.k,
+                                      frame_idx=self.ambig_idx, n_idx=n_ambig,
+                                      out_dist=self.new_dist, out_assign=self.new_assign,
+                                      scatter=True, workspace=self._tc_ws)
+            else:
+                _ops.assign_device(self.metric, self.data, self.medoids,
+                                   frame_idx=self.ambig_idx, n_idx=n_ambig,
+                                   out_dist=self.new_dist, out_assign=self.new_assign,
+                                   accumulate=False, scatter=True, k=self.k)
             new_num = self._sumsq(self.new_dist)
+            if self._ctx.use_list:
+                # data without cluster structure: after a few overflows stop listing
+                self._list_overflows += 1
+                if self._list_overflows >= 4:
+                    self._ctx.use_list = 0
         if prop_global is None:
             prop_global = int(scal[0])
         old_cost = self.cost_num / self.n_global
@@ -414,7 +438,8 @@ class PamEngine:
             # Every TC_AUDIT_EVERY-th proposal (and any profiled one) takes the step-by-step
             # path below, whose synchronous screen call also runs the audit; all others are
             # queued by ONE C call and cost one stream synchronisation.
-            fast = (self._ctx is not None and prof is None and self.counts_by_rank is not None
+            fast = (self._ctx is not None and self.prune and self.prune_compact
+                    and prof is None and self.counts_by_rank is not None
                     and ((self._proposals_done + 1) % _ops.TC_AUDIT_EVERY != 0
                          or _ops._audit_level() == 0))
             if fast:

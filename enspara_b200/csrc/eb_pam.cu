@@ -11,6 +11,7 @@
 // All kernels are HBM bound over 4..8-byte-per-frame vectors; they exist so that distances and
 // assignments never leave the device between proposals.
 #include "eb_common.cuh"
+#include "eb_rmsd.cuh"
 
 namespace eb {
 
@@ -278,6 +279,190 @@ __global__ void k_global_index(const int64_t *local, int64_t offset, int64_t *ou
     out[0] = local[0] + offset;
 }
 
+// ------------------------------------------------------------------------------------------
+// Re-assignment of a proposal's ambiguous frames (kmedoids.py:666-670) against the medoids the
+// triangle inequality leaves.  RMSD is a metric: d(x, m_j) >= d(p, m_j) - d(x, p), so medoid j
+// can only win (or tie) frame x if cc[j] = d(p, m_j) < 2 d(x, p); with the float margin of
+// k_pam_need_list the test is !(d(x, p) <= 0.499995f * cc[j]).  d(x, p) is new_ctr_dist[x]
+// (the full pass) and is exactly what slot cid -- now holding p -- would score.
+// k_pam_medoid_list: ascending list of the medoids that pass the test for the LARGEST d(x, p)
+// of the subset (one block; more than `cap` -> overflow, the caller takes the general path).
+// k_pam_reassign_listed: one warp per ambiguous frame; the listed medoids that pass the
+// frame's own test are scored exactly (the arithmetic of the exact kernel / re-score: same
+// lanes, same atom order, same QCP) by the warp's four 8-lane groups; the nearest of those and
+// (d(x, p), cid) wins, lowest index on ties.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_pam_medoid_list(const int64_t *__restrict__ ambig_idx, const int64_t *__restrict__ n_ambig,
+                  const float *__restrict__ new_ctr_dist, const float *__restrict__ cc, int k,
+                  int cid, int cap, int32_t *list, int32_t *list_n, int32_t *ovf)
+{
+    __shared__ float s_max[32];
+    __shared__ int s_cnt[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long m = (long)*n_ambig;
+    float dmax = 0.0f;
+    for (long p = tid; p < m; p += 1024) dmax = fmaxf(dmax, new_ctr_dist[ambig_idx[p]]);
+#pragma unroll
+    for (int msk = 16; msk > 0; msk >>= 1)
+        dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, msk));
+    if (lane == 0) s_max[warp] = dmax;
+    __syncthreads();
+    dmax = s_max[0];
+    for (int w = 1; w < 32; ++w) dmax = fmaxf(dmax, s_max[w]);
+    int base = 0;
+    for (int j0 = 0; j0 < k; j0 += 1024) {
+        const int j = j0 + tid;
+        const bool keep = j < k && j != cid && !(dmax <= 0.499995f * cc[j]);
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_cnt[warp] = __popc(mask);
+        __syncthreads();
+        int pre = 0, total = 0;
+        for (int w = 0; w < 32; ++w) {
+            const int c = s_cnt[w];
+            if (w < warp) pre += c;
+            total += c;
+        }
+        const int pos = base + pre + __popc(mask & ((1u << lane) - 1u));
+        if (keep && pos < cap) list[pos] = j;
+        base += total;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        if (base > cap) {
+            *list_n = 0;
+            atomicAdd(ovf, 1);
+        } else {
+            *list_n = base;
+        }
+    }
+}
+
+constexpr int kListWarps = 4;
+constexpr int kListThreads = kListWarps * 32;
+
+__global__ void __launch_bounds__(kListThreads, 4)
+k_pam_reassign_listed(const float *__restrict__ xyz, const double *__restrict__ traces,
+                      int n_atoms, int A_pad, const float *__restrict__ centers,
+                      const double *__restrict__ ctraces,
+                      const int64_t *__restrict__ ambig_idx, const int64_t *__restrict__ n_ambig,
+                      const float *__restrict__ new_ctr_dist, const float *__restrict__ cc,
+                      int cid, const int32_t *__restrict__ list,
+                      const int32_t *__restrict__ list_n, int cap, float *new_dist,
+                      int32_t *new_assign)
+{
+    // One WARP per ambiguous frame, warps independent of each other (no block barrier): a
+    // frame costs a chain of dependent latencies (index, distance, list, coordinates) whatever
+    // the number of survivors, so what matters is how many frames are in flight per SM
+    // (a block per frame: 4-5; this form: 16).
+    extern __shared__ int cl_all[];                      // [kListWarps][cap]
+    const long m = (long)*n_ambig;
+    const int ln = *list_n;
+    const int lane = threadIdx.x & 31, l8 = lane & 7, g = lane >> 3, warp = threadIdx.x >> 5;
+    int *cl = cl_all + (size_t)warp * cap;
+    const int A4 = A_pad >> 2;
+    const size_t stride = 3 * (size_t)A_pad;
+    const long warps_total = (long)gridDim.x * kListWarps;
+    for (long p = (long)blockIdx.x * kListWarps + warp; p < m; p += warps_total) {
+        const long f = (long)ambig_idx[p];
+        const float dn = new_ctr_dist[f];
+        // the listed medoids that pass this frame's own test, in list (= index) order
+        int cnt = 0;
+        for (int i0 = 0; i0 < ln; i0 += 32) {
+            const int i = i0 + lane;
+            const int j = i < ln ? list[i] : 0;
+            const bool keep = i < ln && !(dn <= 0.499995f * __ldg(cc + j));
+            const unsigned mask = __ballot_sync(0xffffffffu, keep);
+            if (keep) cl[cnt + __popc(mask & ((1u << lane) - 1u))] = j;
+            cnt += __popc(mask);
+        }
+        __syncwarp();
+        const float4 *px = reinterpret_cast<const float4 *>(xyz + (size_t)f * stride);
+        const double Ga = traces[f];
+        float best_d = INFINITY;
+        int best_c = 0x7fffffff;
+        // two candidates per group share the frame's loads; with at most 4 survivors one
+        // candidate per group keeps twice as many groups busy
+        const int per = cnt > 4 ? 2 : 1;
+        for (int base = 0; base < cnt; base += per * 4) {
+            const int i0 = base + per * g;
+            const bool act0 = i0 < cnt, act1 = per == 2 && i0 + 1 < cnt;
+            const int c0 = act0 ? cl[i0] : 0, c1 = act1 ? cl[i0 + 1] : c0;
+            const float4 *p0 = reinterpret_cast<const float4 *>(centers + (size_t)c0 * stride);
+            const float4 *p1 = reinterpret_cast<const float4 *>(centers + (size_t)c1 * stride);
+            double m0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, m1[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            if (act1) {
+#pragma unroll 2
+                for (int j = l8; j < A4; j += 8) {
+                    const float4 x = __ldg(px + j), y = __ldg(px + A4 + j),
+                                 z = __ldg(px + 2 * A4 + j);
+                    const float4 ax = __ldg(p0 + j), ay = __ldg(p0 + A4 + j),
+                                 az = __ldg(p0 + 2 * A4 + j);
+                    const float4 bx = __ldg(p1 + j), by = __ldg(p1 + A4 + j),
+                                 bz = __ldg(p1 + 2 * A4 + j);
+                    acc_atom(m0, x.x, y.x, z.x, (double)ax.x, (double)ay.x, (double)az.x);
+                    acc_atom(m0, x.y, y.y, z.y, (double)ax.y, (double)ay.y, (double)az.y);
+                    acc_atom(m0, x.z, y.z, z.z, (double)ax.z, (double)ay.z, (double)az.z);
+                    acc_atom(m0, x.w, y.w, z.w, (double)ax.w, (double)ay.w, (double)az.w);
+                    acc_atom(m1, x.x, y.x, z.x, (double)bx.x, (double)by.x, (double)bz.x);
+                    acc_atom(m1, x.y, y.y, z.y, (double)bx.y, (double)by.y, (double)bz.y);
+                    acc_atom(m1, x.z, y.z, z.z, (double)bx.z, (double)by.z, (double)bz.z);
+                    acc_atom(m1, x.w, y.w, z.w, (double)bx.w, (double)by.w, (double)bz.w);
+                }
+            } else if (act0) {
+#pragma unroll 4
+                for (int j = l8; j < A4; j += 8) {
+                    const float4 x = __ldg(px + j), y = __ldg(px + A4 + j),
+                                 z = __ldg(px + 2 * A4 + j);
+                    const float4 ax = __ldg(p0 + j), ay = __ldg(p0 + A4 + j),
+                                 az = __ldg(p0 + 2 * A4 + j);
+                    acc_atom(m0, x.x, y.x, z.x, (double)ax.x, (double)ay.x, (double)az.x);
+                    acc_atom(m0, x.y, y.y, z.y, (double)ax.y, (double)ay.y, (double)az.y);
+                    acc_atom(m0, x.z, y.z, z.z, (double)ax.z, (double)ay.z, (double)az.z);
+                    acc_atom(m0, x.w, y.w, z.w, (double)ax.w, (double)ay.w, (double)az.w);
+                }
+            }
+            group8_reduce(m0);
+            if (per == 2) group8_reduce(m1);
+            if (act0) {
+                const float d = rmsd_from_msd(qcp_msd(m0, Ga, ctraces[c0], n_atoms));
+                if (d < best_d || (d == best_d && c0 < best_c)) {
+                    best_d = d;
+                    best_c = c0;
+                }
+            }
+            if (act1) {
+                const float d = rmsd_from_msd(qcp_msd(m1, Ga, ctraces[c1], n_atoms));
+                if (d < best_d || (d == best_d && c1 < best_c)) {
+                    best_d = d;
+                    best_c = c1;
+                }
+            }
+        }
+        // nearest over the four groups, then against (d(x, p), cid): slot cid holds the proposal
+#pragma unroll
+        for (int msk = 8; msk < 32; msk <<= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, best_d, msk);
+            const int oc = __shfl_xor_sync(0xffffffffu, best_c, msk);
+            if (od < best_d || (od == best_d && oc < best_c)) {
+                best_d = od;
+                best_c = oc;
+            }
+        }
+        if (lane == 0) {
+            float bd = dn;
+            int bc = cid;
+            if (best_d < bd || (best_d == bd && best_c < bc)) {
+                bd = best_d;
+                bc = best_c;
+            }
+            new_dist[f] = bd;
+            new_assign[f] = bc;
+        }
+        __syncwarp();
+    }
+}
+
 static int pam_blocks(long n)
 {
     long b = (n + kPamThreads * 4 - 1) / (kPamThreads * 4);
@@ -442,7 +627,23 @@ int eb_pam_propose_rmsd(const eb_pam_ctx *c, int32_t cid, int64_t kth, int64_t m
                                       c->prop_idx, c->tc_ovf);
         EB_LAUNCH_CHECK();
         // ambiguous frames against all medoids (kmedoids.py:666-670)
-        if (m_max > 0) {
+        if (m_max > 0 && c->use_list) {
+            EB_CHECK_ARG(c->med_list && c->med_list_n && c->med_list_cap > 0 && c->tc_ovf &&
+                             c->med_list_cap <= 2048,
+                         "pam_propose: missing medoid list");
+            k_pam_medoid_list<<<1, 1024, 0, s>>>(c->ambig_idx, c->scal_i + 1, c->new_ctr_dist,
+                                                 c->cc, c->k, cid, c->med_list_cap, c->med_list,
+                                                 c->med_list_n, c->tc_ovf);
+            EB_LAUNCH_CHECK();
+            long blocks = (m_max + kListWarps - 1) / kListWarps;
+            if (blocks > 4L * sm_count()) blocks = 4L * sm_count();
+            k_pam_reassign_listed<<<(int)blocks, kListThreads,
+                                    sizeof(int) * (size_t)kListWarps * c->med_list_cap, s>>>(
+                c->xyz, c->traces, c->n_atoms, rmsd_apad(c->n_atoms), c->medoid_xyz,
+                c->medoid_traces, c->ambig_idx, c->scal_i + 1, c->new_ctr_dist, c->cc, cid,
+                c->med_list, c->med_list_n, c->med_list_cap, c->new_dist, c->new_assign);
+            EB_LAUNCH_CHECK();
+        } else if (m_max > 0) {
             if (c->use_tc) {
                 EB_CHECK_ARG(c->tc_cand && c->tc_scratch && c->tc_ovf,
                              "pam_propose: missing screen workspace");
@@ -496,6 +697,11 @@ int eb_pam_restore_medoid(const eb_pam_ctx *c, int32_t cid, void *stream)
                                      (long)frame_floats);
     EB_LAUNCH_CHECK();
     return EB_OK;
+}
+
+size_t eb_struct_bytes(int which)
+{
+    return which == 0 ? sizeof(eb_kc_state) : which == 1 ? sizeof(eb_pam_ctx) : 0;
 }
 
 }  // extern "C"

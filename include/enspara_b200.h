@@ -303,7 +303,14 @@ int eb_select_member(const int32_t *assign, int64_t n, int32_t cid, int64_t kth,
  *                  scal_i = {prop_idx, n_ambig}; medoid cid saved and replaced by the proposal;
  *                  the ambiguous frames (at most m_max, real count on the device) re-assigned
  *                  against all k medoids (tensor-core screen + exact re-score when use_tc, else
- *                  the exact kernel); scal_d = sum(new_dist^2);
+ *                  the exact kernel) -- or, with use_list, against the medoids the triangle
+ *                  inequality leaves: medoid j can only win frame x if d(proposal, m_j) <
+ *                  2 d(x, proposal), and both numbers are already known (cc and new_ctr_dist),
+ *                  so the listed medoids (a few per cent of k on clustered data) are scored
+ *                  exactly and everything else is skipped; same result.  More than
+ *                  med_list_cap listed medoids count as an overflow in tc_ovf and the caller
+ *                  re-assigns the subset itself;
+ *                  scal_d = sum(new_dist^2);
  *   EB_PAM_READBACK scal_d, scal_i and tc_ovf copied to pin_d / pin_i / pin_o (asynchronous;
  *                  the caller synchronises the stream once).
  * eb_pam_restore_medoid puts the saved medoid back after a rejected proposal. */
@@ -346,10 +353,16 @@ typedef struct eb_pam_ctx {
     double *pin_d;               /* pinned host: (1), (2), (1) */
     int64_t *pin_i;
     int32_t *pin_o;
+    int32_t *med_list;           /* (med_list_cap) medoids that can still win an ambiguous frame */
+    int32_t *med_list_n;         /* (1) */
+    int32_t med_list_cap;
+    int32_t use_list;            /* re-assign the ambiguous frames against med_list only */
 } eb_pam_ctx;
 int eb_pam_propose_rmsd(const eb_pam_ctx *ctx, int32_t cid, int64_t kth, int64_t m_max,
                         int stages, void *stream);
 int eb_pam_restore_medoid(const eb_pam_ctx *ctx, int32_t cid, void *stream);
+/* sizeof(eb_kc_state) / sizeof(eb_pam_ctx) as compiled: a binding checks its struct mirrors */
+size_t eb_struct_bytes(int which /* 0: eb_kc_state, 1: eb_pam_ctx */);
 
 /* ---- trajectory input without mdtraj: native GROMACS .xtc reader (host code) -------------
  * Replaces md.load(path, stride=, atom_indices=) for .xtc files in the loaders either side of

@@ -72,3 +72,13 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(ImportError):
         _lib.load()
+
+
+def test_struct_mirrors_match_the_compiled_layout():
+    """ctypes mirrors of eb_kc_state / eb_pam_ctx have the size the library was compiled with
+    (host-only call: no GPU needed)."""
+    import ctypes
+    from enspara_b200 import _lib
+    lib = _lib.load()
+    assert lib.eb_struct_bytes(0) == ctypes.sizeof(_lib.KcState) == 64
+    assert lib.eb_struct_bytes(1) == ctypes.sizeof(_lib.PamCtx)

@@ -227,7 +227,8 @@ def test_kmedoids_input_errors(cuda):
 
 def test_pam_pruned_full_pass_changes_nothing(cuda):
     """The triangle-inequality pruning of the PAM full pass (frames that provably stay with
-    their medoid are not read) gives bit-identical sweeps."""
+    their medoid are not read) gives bit-identical sweeps, and so does queueing a whole
+    proposal with one C call instead of step by step."""
     from enspara_b200 import synth
     from enspara_b200.cluster import kcenters, util
     from enspara_b200.cluster._pam import PamEngine
@@ -238,12 +239,26 @@ def test_pam_pruned_full_pass_changes_nothing(cuda):
         r = kcenters.kcenters(data, "rmsd", n_clusters=k)
         ctr = [int(c) for c in r.center_indices]
         out = []
-        for prune, compact in ((True, True), (True, False), (False, False)):
-            # compact-list pruned pass (default), fused skip-rounds pruned pass, full pass
+        for prune, compact, one_call, med_list in (
+                (True, True, True, "list"), (True, True, True, "all"),
+                (True, True, True, "cap1"), (True, True, False, None),
+                (True, False, False, None), (False, False, False, None)):
+            # default: the whole proposal queued by ONE C call (eb_pam_propose_rmsd) with the
+            # ambiguous frames re-assigned against the medoids the triangle inequality leaves;
+            # the same call against all medoids; a medoid list of capacity 1 (overflows ->
+            # general path, then the engine stops listing); then the steps issued one by one
+            # from Python, the fused skip-rounds pruned pass, and the unpruned full pass
             pam = PamEngine(data, util.RMSD, _SingleComm(), r.distances, r.assignments, ctr)
-            assert pam.prune and pam.prune_compact
+            assert pam.prune and pam.prune_compact and pam._ctx is not None
+            assert pam._ctx.use_list == 1
             pam.prune = prune
             pam.prune_compact = compact
+            if med_list == "all":
+                pam._ctx.use_list = 0
+            elif med_list == "cap1":
+                pam._ctx.med_list_cap = 1
+            if not one_call:
+                pam._ctx = None
             log = []
             for sweep in range(2):
                 pam.sweep(random_state=sweep, log=log)
