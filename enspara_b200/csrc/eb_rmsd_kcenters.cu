@@ -478,6 +478,10 @@ k_kcenters_multi_rmsd(const float *__restrict__ xyz, const double *__restrict__ 
              chunk += warps_total) {
             const long base = chunk * FPC;
             const long f = (lane < FPC) ? base + lane : n;
+            // requested before the inner products so that their latency hides behind them
+            // (the same lane wrote dist[f] in the previous iteration: static chunk -> warp map)
+            const double Ga_f = (f < n) ? traces[f] : 0.0;
+            const float old = (f < n) ? dist[f] : 0.0f;
 #pragma unroll 1
             for (int s = 0; s < ROUNDS; ++s) {
                 const long fs = base + 4 * s + g;
@@ -497,8 +501,7 @@ k_kcenters_multi_rmsd(const float *__restrict__ xyz, const double *__restrict__ 
                 const double *srcm = my_sums + lane * kSumStride;
 #pragma unroll
                 for (int e = 0; e < 9; ++e) m[e] = srcm[e];
-                const float d = rmsd_from_msd(qcp_msd(m, traces[f], Gb, A));
-                const float old = dist[f];
+                const float d = rmsd_from_msd(qcp_msd(m, Ga_f, Gb, A));
                 if (d < old) {  // strict '<', kcenters.py:304
                     dist[f] = d;
                     assign[f] = k;
