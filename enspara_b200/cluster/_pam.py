@@ -453,18 +453,7 @@ class PamEngine:
                         self._refresh_counts()
                 continue
             if proposals is None:
-                n_states = self._member_counts(cid)
-                total = int(n_states.sum())
-                if total < 1:
-                    raise ValueError("'a' cannot be empty unless no samples are taken")
-                g = int(rs.randint(total))
-                if striped_randind and sh.size > 1:
-                    concat = np.concatenate([np.arange(total)[r::sh.size]
-                                             for r in range(sh.size)])
-                    g = int(np.where(concat == g)[0][0])
-                bounds = np.concatenate([[0], np.cumsum(n_states)])
-                owner = int(np.searchsorted(bounds, g, side="right") - 1)
-                kth = g - int(bounds[owner])
+                owner, kth = self._draw_member(cid, rs, striped_randind)
                 if sh.rank == owner:
                     _lib.call("eb_select_member", ptr(self.assign), self.n, cid, kth,
                               ptr(self.scal_i), ptr(self.scratch), stream_ptr())

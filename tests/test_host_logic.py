@@ -145,3 +145,41 @@ def test_timed_logs_elapsed_seconds():
         with timed("never %.1f", seen.append):
             raise ValueError("x")
     assert len(seen) == 1
+
+
+def test_pam_draw_member_consumes_the_reference_stream():
+    """PamEngine._draw_member (host only): one randint(total) per proposal like
+    random_state.choice(state_inds) (kmedoids.py:514); sharded: the k-th member
+    in GLOBAL frame order maps to (owner rank, k-th member on the owner), or through the
+    reference's striped concatenation (mpi/ops.py:256-268) with striped_randind."""
+    from types import SimpleNamespace
+    from enspara_b200.cluster._pam import PamEngine
+    eng = PamEngine.__new__(PamEngine)
+    # single rank: cluster 0 has 7 members
+    eng.shard = SimpleNamespace(size=1, rank=0)
+    eng.counts_by_rank = np.array([[7, 3]])
+    rs, ref = np.random.RandomState(5), np.random.RandomState(5)
+    for _ in range(20):
+        assert eng._draw_member(0, rs, False) == (0, int(ref.randint(7)))
+    assert rs.randint(1 << 30) == ref.randint(1 << 30)        # streams still aligned
+    # three ranks holding 2, 0 and 5 members of cluster 1
+    eng.shard = SimpleNamespace(size=3, rank=1)
+    eng.counts_by_rank = np.array([[1, 2], [1, 0], [1, 5]])
+    rs, ref = np.random.RandomState(9), np.random.RandomState(9)
+    seen = set()
+    for _ in range(200):
+        g = int(ref.randint(7))
+        owner, kth = eng._draw_member(1, rs, False)
+        assert (owner, kth) == ((0, g) if g < 2 else (2, g - 2))
+        seen.add((owner, kth))
+    assert len(seen) == 7 and all(o != 1 for o, _ in seen)     # the empty rank never owns
+    # striped map: position of g in concat(arange(total)[r::size])
+    rs, ref = np.random.RandomState(3), np.random.RandomState(3)
+    concat = np.concatenate([np.arange(7)[r::3] for r in range(3)])
+    for _ in range(50):
+        g = int(np.where(concat == int(ref.randint(7)))[0][0])
+        assert eng._draw_member(1, rs, True) == ((0, g) if g < 2 else (2, g - 2))
+    # an empty cluster is the reference's ValueError (np.random.choice on an empty array)
+    eng.counts_by_rank = np.array([[0, 2], [0, 0], [0, 5]])
+    with pytest.raises(ValueError):
+        eng._draw_member(0, rs, False)
