@@ -239,7 +239,7 @@ __device__ __forceinline__ void qcp4_f32(const float M[4][9], const float g[4], 
     }
 }
 // slack for the FP32 solve, relative to (Ga+Gb)/2, in units of N*msd (measured: < 8e-6)
-constexpr double kQcpSlack = 6.4e-5;
+constexpr float kQcpSlackF = 6.8e-5f;   // 6.4e-5 + 4e-6 for the FP32 rounding of the bound arithmetic
 
 struct Smem {
     uint64_t full[STAGES];
@@ -385,10 +385,16 @@ k_tc_screen(const unsigned char *__restrict__ a_img, const unsigned char *__rest
             const long f = ft * BM + row;
             const bool fvalid = f < n;
             const double Ga = fvalid ? traces[frame_idx ? frame_idx[f] : f] : 0.0;
-            const float sa = sqrtf((float)Ga);
+            const float gaf = (float)Ga;
+            const float sa = sqrtf(gaf);
+            const float kappaf = (float)kappa * 1.000001f;
             // screen state of this (frame, list): thread-private across the centre tiles; all
-            // bounds are kept in units of N * msd
-            double umin = 1e300;
+            // bounds are kept in units of N * msd.  FP32 throughout: the rounding of
+            // v = 2 (half - sc * lam) is <= 3e-7 * half, two orders below the slack that is
+            // added anyway (kQcpSlackF carries an extra 4e-6 for it); the float64 version of
+            // this bookkeeping (DADD / DMUL / DSETP / F2F) held 36 % of the kernel's stall
+            // samples for 5 % of its instructions.
+            float umin = 3.0e38f;
             int ncand = 0;
             const int lid = seg * EPI_PARTS + part;
             const size_t slot = ((size_t)(fvalid ? f : 0) * n_lists + lid) * MAX_CAND;
@@ -441,17 +447,17 @@ k_tc_screen(const unsigned char *__restrict__ a_img, const unsigned char *__rest
                     }
 #pragma unroll
                     for (int bq = 0; bq < (MODE == 1 ? 2 : 0); ++bq) {   // two batches of four
-                        float Mn[4][9], gq[4], scf[4], lam[4], dl[4];
-                        double Gb[4];
+                        float Mn[4][9], gq[4], scf[4], lam[4], dl[4], halff[4];
 #pragma unroll
                         for (int p = 0; p < 4; ++p) {
                             const int cc = bq * 4 + p;
                             const int c = min(ct * NC + g * 8 + cc, k - 1);
-                            Gb[p] = __ldg(ctraces + c);
-                            scf[p] = fmaxf(sa * sqrtf((float)Gb[p]), 1e-30f);
+                            const float gbf = (float)__ldg(ctraces + c);
+                            scf[p] = fmaxf(sa * sqrtf(gbf), 1e-30f);
                             const float inv = __frcp_rn(scf[p]);
                             const float inv_acc = inv * kAccumUnscale;   // accumulators: 2^16 M
-                            gq[p] = (float)(0.5 * (Ga + Gb[p])) * inv;
+                            halff[p] = 0.5f * (gaf + gbf);
+                            gq[p] = halff[p] * inv;
 #pragma unroll
                             for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -463,10 +469,10 @@ k_tc_screen(const unsigned char *__restrict__ a_img, const unsigned char *__rest
                         for (int p = 0; p < 4; ++p) {
                             const int c = ct * NC + g * 8 + bq * 4 + p;
                             if (!fvalid || c >= k) continue;
-                            const double half = 0.5 * (Ga + Gb[p]);
-                            const double sc = (double)scf[p];
-                            const double v = 2.0 * (half - sc * (double)lam[p]);  // N * msd
-                            const double e = kappa * sc + kQcpSlack * half;
+                            const float half = halff[p];
+                            const float sc = scf[p];
+                            const float v = 2.0f * __fmaf_rn(-sc, lam[p], half);  // N * msd
+                            const float e = __fmaf_rn(kappaf, sc, kQcpSlackF * half);
                             // Newton from above decreases monotonically towards lambda_max, so
                             // an unsettled solve still OVER-estimates lambda: v - e stays a valid
                             // lower bound, only the upper bound needs a settled solve.  A solve
@@ -474,12 +480,12 @@ k_tc_screen(const unsigned char *__restrict__ a_img, const unsigned char *__rest
                             const bool finite = (lam[p] == lam[p]) && lam[p] <= gq[p] * 1.001f &&
                                                 lam[p] >= -gq[p];
                             const bool settled = fabsf(dl[p]) <= 4e-6f * fabsf(gq[p]);
-                            const double lo = finite ? v - e : -1e300;
-                            const double up = (finite && settled) ? v + e : 1e300;
+                            const float lo = finite ? v - e : -3.0e38f;
+                            const float up = (finite && settled) ? v + e : 3.0e38f;
                             if (lo <= umin) {
                                 if (ncand < MAX_CAND) {
                                     cand_list[slot + ncand] = c;
-                                    cand_bound[slot + ncand] = __double2float_rd(lo);
+                                    cand_bound[slot + ncand] = lo;
                                 }
                                 ++ncand;
                             }
@@ -490,7 +496,7 @@ k_tc_screen(const unsigned char *__restrict__ a_img, const unsigned char *__rest
                                 for (int s2 = 0; s2 < MAX_CAND; ++s2) {
                                     const float b = cand_bound[slot + s2];
                                     const int cs = cand_list[slot + s2];
-                                    if ((double)b <= umin) {
+                                    if (b <= umin) {
                                         cand_list[slot + w] = cs;
                                         cand_bound[slot + w] = b;
                                         ++w;
@@ -498,7 +504,7 @@ k_tc_screen(const unsigned char *__restrict__ a_img, const unsigned char *__rest
                                 }
                                 if (w < MAX_CAND) {
                                     cand_list[slot + w] = c;
-                                    cand_bound[slot + w] = __double2float_rd(lo);
+                                    cand_bound[slot + w] = lo;
                                     ncand = w + 1;
                                 } else {
                                     ncand = MAX_CAND + 2;  // sticky overflow: exact fallback
@@ -509,7 +515,7 @@ k_tc_screen(const unsigned char *__restrict__ a_img, const unsigned char *__rest
                 }
             }
             if (MODE == 1 && fvalid) {
-                cand_umin[(size_t)f * n_lists + lid] = __double2float_ru(fmin(umin, 3.0e38));
+                cand_umin[(size_t)f * n_lists + lid] = umin;
                 if (ncand > MAX_CAND) {
                     cand_count[(size_t)f * n_lists + lid] = -1;  // overflow -> exact path (host)
                 } else {
@@ -517,7 +523,7 @@ k_tc_screen(const unsigned char *__restrict__ a_img, const unsigned char *__rest
                     for (int s2 = 0; s2 < ncand; ++s2) {
                         const float b = cand_bound[slot + s2];
                         const int cs = cand_list[slot + s2];
-                        if ((double)b <= umin) {
+                        if (b <= umin) {
                             cand_list[slot + w] = cs;
                             cand_bound[slot + w] = b;
                             ++w;
