@@ -400,6 +400,14 @@ k_tc_screen(const unsigned char *__restrict__ a_img, const unsigned char *__rest
             const size_t slot = ((size_t)(fvalid ? f : 0) * n_lists + lid) * MAX_CAND;
             for (int ct = seg * ct_per_seg; ct < ct_hi; ++ct, ++tile_no) {
                 const uint32_t as = tile_no % ACC_SETS;
+                // the traces of this warp's 16 centres (and their square roots), one per lane,
+                // fetched while the tile's MMAs still run; the pair loop broadcasts them with
+                // shuffles instead of every lane loading and converting the same value
+                float my_gb = 0.f, my_sq = 0.f;
+                if (lane < 16) {
+                    my_gb = (float)__ldg(ctraces + min(ct * NC + part * 16 + lane, k - 1));
+                    my_sq = sqrtf(my_gb);
+                }
                 mbar_wait(&sm->tmem_full[as], (tile_no / ACC_SETS) & 1u);
                 tc_fence_after();
                 const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) +
@@ -451,9 +459,9 @@ k_tc_screen(const unsigned char *__restrict__ a_img, const unsigned char *__rest
 #pragma unroll
                         for (int p = 0; p < 4; ++p) {
                             const int cc = bq * 4 + p;
-                            const int c = min(ct * NC + g * 8 + cc, k - 1);
-                            const float gbf = (float)__ldg(ctraces + c);
-                            scf[p] = fmaxf(sa * sqrtf(gbf), 1e-30f);
+                            const float gbf = __shfl_sync(0xffffffffu, my_gb, gg * 8 + cc);
+                            const float sqg = __shfl_sync(0xffffffffu, my_sq, gg * 8 + cc);
+                            scf[p] = fmaxf(sa * sqg, 1e-30f);
                             const float inv = __frcp_rn(scf[p]);
                             const float inv_acc = inv * kAccumUnscale;   // accumulators: 2^16 M
                             halff[p] = 0.5f * (gaf + gbf);
