@@ -234,15 +234,18 @@ def test_pam_pruned_full_pass_changes_nothing(cuda):
     from enspara_b200.cluster._pam import PamEngine
     from enspara_b200.cluster.kcenters import _SingleComm
     from enspara_b200.device import DeviceTrajectory
-    for n, A, k in ((6000, 40, 50), (3000, 22, 100), (501, 22, 7)):
+    all_forms = ((True, True, True, "list"), (True, True, True, "all"),
+                 (True, True, True, "cap1"), (True, True, False, None),
+                 (True, False, False, None), (False, False, False, None))
+    # the last case has more medoids than one 1024-wide chunk of the list kernel, and more than
+    # the list's capacity
+    for n, A, k, forms in ((6000, 40, 50, all_forms), (3000, 22, 100, all_forms),
+                           (501, 22, 7, all_forms), (12000, 22, 1300, all_forms[:2])):
         data = DeviceTrajectory.from_host(synth.trajectory(n, A, seed=n))
         r = kcenters.kcenters(data, "rmsd", n_clusters=k)
         ctr = [int(c) for c in r.center_indices]
         out = []
-        for prune, compact, one_call, med_list in (
-                (True, True, True, "list"), (True, True, True, "all"),
-                (True, True, True, "cap1"), (True, True, False, None),
-                (True, False, False, None), (False, False, False, None)):
+        for prune, compact, one_call, med_list in forms:
             # default: the whole proposal queued by ONE C call (eb_pam_propose_rmsd) with the
             # ambiguous frames re-assigned against the medoids the triangle inequality leaves;
             # the same call against all medoids; a medoid list of capacity 1 (overflows ->
@@ -260,7 +263,7 @@ def test_pam_pruned_full_pass_changes_nothing(cuda):
             if not one_call:
                 pam._ctx = None
             log = []
-            for sweep in range(2):
+            for sweep in range(2 if k < 1000 else 1):
                 pam.sweep(random_state=sweep, log=log)
             a, d = pam.results_host()
             out.append((list(pam.medoid_global), a, d, log))
