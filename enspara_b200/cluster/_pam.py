@@ -90,8 +90,14 @@ class PamEngine:
         self._pin_d = self._pin_all[0:1].view(torch.float64)
         self._pin_i = self._pin_all[1:3]
         self._pin_o = self._pin_all[3:4].view(torch.int32)[0:1]
+        # zero-copy numpy views of the same pinned block: reading a scalar through torch
+        # indexing costs microseconds per element, through numpy ~0.1 us
+        self._np_i64 = self._pin_all.numpy()
+        self._np_f64 = self._pin_all.view(torch.float64).numpy()
+        self._np_i32 = self._pin_all.view(torch.int32).numpy()
         self.host_issue_s = 0.0
         self.sync_wait_s = 0.0
+        self.refresh_s = 0.0
         self._t_proposal = time.perf_counter()
         # RMSD with pruning: the whole proposal is queued by ONE C call (eb_pam_propose_rmsd);
         # the per-step Python path below stays for feature metrics, profiling and the
@@ -200,6 +206,11 @@ class PamEngine:
         """Member counts of every cluster on every rank (len(np.where(assignments == cid)[0]),
         kmedoids.py:611).  Assignments only change when a proposal is accepted, so the counts
         are cached on the host between acceptances (one histogram launch + one small D2H)."""
+        t0 = time.perf_counter()
+        self._refresh_counts_impl()
+        self.refresh_s += time.perf_counter() - t0
+
+    def _refresh_counts_impl(self):
         _lib.call("eb_count_members", ptr(self.assign), self.n, self.k, ptr(self.counts),
                   stream_ptr())
         if self.shard.size > 1:
@@ -268,6 +279,9 @@ class PamEngine:
         self._ctx_ref = ctypes.byref(c)
         self._ctx = c
         self._ctx_state()
+        fn, self._restore = self.lib.eb_pam_propose_rmsd, self.lib.eb_pam_restore_medoid
+        check = _lib.check
+        self._propose = lambda *a: check(fn(*a))
         return c
 
     def _ctx_state(self):
@@ -311,14 +325,14 @@ class PamEngine:
             self._pin_d2.copy_(t, non_blocking=True)
             self._pin_i.copy_(self.scal_i, non_blocking=True)
         t0 = time.perf_counter()
-        torch.cuda.current_stream().synchronize()
+        self._stream.synchronize()
         t1 = time.perf_counter()
         self.host_issue_s += t0 - self._t_proposal
         self.sync_wait_s += t1 - t0
+        scal = (int(self._np_i64[1]), int(self._np_i64[2]))
         if sharded:
-            return float(self._pin_d2[0]), self._pin_i.clone(), int(self._pin_d2[1])
-        return (float(self._pin_d[0]), self._pin_i.clone(),
-                int(self._pin_o[0]) if with_ovf else 0)
+            return float(self._pin_d2[0]), scal, int(self._pin_d2[1])
+        return float(self._np_f64[0]), scal, (int(self._np_i32[6]) if with_ovf else 0)
 
     def _draw_member(self, cid, rs, striped_randind):
         """(owner rank, k-th member on the owner) of a random member of cluster cid, consuming
@@ -342,8 +356,9 @@ class PamEngine:
         """One proposal through eb_pam_propose_rmsd.  Returns ((accepted, old_cost, new_cost,
         accepted), proposal's global index) -- the tuple's tail is what the sweep logs."""
         sh = self.shard
-        call, ctx, stream = _lib.call, self._ctx_ref, stream_ptr()
-        m_max = int(self._member_counts(cid)[sh.rank])
+        ctx, stream = self._ctx_ref, self._stream_ptr
+        call = self._propose
+        m_max = int(self.counts_by_rank[sh.rank, cid])
         use_tc = self._ctx_workspace(m_max)
         stages = _lib.PAM_TRIAL
         kth = 0
@@ -354,7 +369,7 @@ class PamEngine:
                 stages |= _lib.PAM_SELECT
             else:
                 if sh.rank == owner:
-                    call("eb_pam_propose_rmsd", ctx, cid, kth, 0, _lib.PAM_SELECT, stream)
+                    call(ctx, cid, kth, 0, _lib.PAM_SELECT, stream)
                 self.comm.broadcast(self.prop_buf, owner)
         else:
             prop_global = int(proposals[cid])
@@ -362,7 +377,7 @@ class PamEngine:
             self._load_proposal(owner, local_idx=loc)
         if sh.size == 1:
             stages |= _lib.PAM_READBACK
-        call("eb_pam_propose_rmsd", ctx, cid, kth, m_max, stages, stream)
+        call(ctx, cid, kth, m_max, stages, stream)
         new_num, scal, n_ovf = self._readback(use_tc)
         if n_ovf > 0:
             # a candidate list (screen) or the medoid list overflowed somewhere: the subset
@@ -396,7 +411,7 @@ class PamEngine:
             self.cost_num = new_num
             self.medoid_global[cid] = prop_global
         else:
-            call("eb_pam_restore_medoid", ctx, cid, stream)
+            _lib.check(self._restore(ctx, cid, stream))
         return (bool(accepted), old_cost, new_cost, bool(accepted)), prop_global
 
     # -- one sweep -----------------------------------------------------------------------
@@ -420,6 +435,9 @@ class PamEngine:
                 rs.set_state(state)
         acceptances = 0
         prof = self.profile          # None, or dict phase -> seconds (developer timing)
+        # the current stream does not change during a sweep: look it up once
+        self._stream = torch.cuda.current_stream()
+        self._stream_ptr = stream_ptr()
 
         def tick(name, t0):
             if prof is None:
@@ -435,12 +453,14 @@ class PamEngine:
         for cid in range(self.k if max_proposals is None else min(self.k, max_proposals)):
             # ---- proposal (kmedoids.py:616-628, 482-517) -------------------------------
             self._t_proposal = time.perf_counter()
-            # Every TC_AUDIT_EVERY-th proposal (and any profiled one) takes the step-by-step
-            # path below, whose synchronous screen call also runs the audit; all others are
-            # queued by ONE C call and cost one stream synchronisation.
+            # Proposals are queued by ONE C call and cost one stream synchronisation.  While
+            # the subset is re-assigned through the tensor-core screen (medoid list off or
+            # given up), every TC_AUDIT_EVERY-th proposal takes the step-by-step path below,
+            # whose synchronous screen call also runs the audit; so does any profiled one.
             fast = (self._ctx is not None and self.prune and self.prune_compact
                     and prof is None and self.counts_by_rank is not None
-                    and ((self._proposals_done + 1) % _ops.TC_AUDIT_EVERY != 0
+                    and (self._ctx.use_list == 1
+                         or (self._proposals_done + 1) % _ops.TC_AUDIT_EVERY != 0
                          or _ops._audit_level() == 0))
             if fast:
                 accepted, prop_global = self._fast_proposal(cid, proposals, rs, striped_randind)

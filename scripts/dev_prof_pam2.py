@@ -20,8 +20,10 @@ t = time.perf_counter()
 pam.sweep(random_state=1, max_proposals=nprop)
 torch.cuda.synchronize()
 wall = (time.perf_counter() - t) / nprop
-print("host issue per proposal: %.1f us; sync wait per proposal: %.1f us" % (
-    1e6 * pam.host_issue_s / (nprop + 20), 1e6 * pam.sync_wait_s / (nprop + 20)))
+print("host issue per proposal: %.1f us; sync wait per proposal: %.1f us; count refresh per "
+      "proposal: %.1f us" % (1e6 * pam.host_issue_s / (nprop + 20),
+                             1e6 * pam.sync_wait_s / (nprop + 20),
+                             1e6 * pam.refresh_s / (nprop + 20)))
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     pam.sweep(random_state=2, max_proposals=nprop)
     torch.cuda.synchronize()
