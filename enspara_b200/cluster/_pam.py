@@ -54,11 +54,14 @@ class PamEngine:
         # scalars read back per proposal: [proposed local index, n_ambig] and [cost numerator]
         # (one 32-byte block {cost f64, proposal i64, n_ambig i64, overflow i32} on the device
         # and in pinned host memory, so the read-back is a single copy)
-        self._scal_all = torch.zeros(4, dtype=torch.int64, device=dev)
+        # followed by the need-list counter, so the three device counters of a proposal
+        # {n_ambig, overflow, n_need} are adjacent and cleared by one memset
+        self._scal_all = torch.zeros(6, dtype=torch.int64, device=dev)
         self.scal_d = self._scal_all[0:1].view(torch.float64)
         self.scal_i = self._scal_all[1:3]
         self._ovf = self._scal_all[3:4].view(torch.int32)[0:1]
-        self.scratch = torch.empty(int(self.lib.eb_pam_scratch_bytes(self.n)),
+        # zero-initialised once: eb_sum_squares keeps a ticket counter behind its partials
+        self.scratch = torch.zeros(int(self.lib.eb_pam_scratch_bytes(self.n)),
                                    dtype=torch.uint8, device=dev)
         self.k = len(medoid_global_inds)
         self.counts = torch.zeros(max(self.k, 1), dtype=torch.int64, device=dev)
@@ -80,7 +83,7 @@ class PamEngine:
         self.prune_compact = True
         if self.prune:
             self.need_idx = torch.empty(max(self.n, 1), dtype=torch.int64, device=dev)
-            self.need_n = torch.zeros(1, dtype=torch.int64, device=dev)
+            self.need_n = self._scal_all[4:5]
             self.need_assign = torch.zeros(max(self.n, 1), dtype=torch.int32, device=dev)
         self.counts_by_rank = None
         self._proposals_done = 0

@@ -90,11 +90,26 @@ k_pam_need_list(const float *__restrict__ dist, const int *__restrict__ assign,
 }
 
 // deterministic sum of squares: fixed block ranges, fixed tree, ordered final pass
+// one warp, fixed order: lane l adds partials l, l+32, ... in sequence, then a fixed shuffle tree
+__device__ __forceinline__ void sum_final_warp(const double *partials, int nb, double *out)
+{
+    const int lane = threadIdx.x;
+    double s = 0.0;
+    for (int b = lane; b < nb; b += 32) s += __ldcg(partials + b);
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) s += shfl_xor_d(s, m);
+    if (lane == 0) *out = s;
+}
+
+// The same partial sums, and the block that finishes last (ticket counter behind the partials,
+// zero between uses) runs the ordered final pass: one launch, the same bits as two.
 template <typename D>
 __global__ void __launch_bounds__(kPamThreads)
-k_sumsq_partial(const D *__restrict__ x, long n, double *__restrict__ partials)
+k_sumsq(const D *__restrict__ x, long n, double *__restrict__ partials, unsigned int *ticket,
+        double *out)
 {
     __shared__ double sh[kPamThreads];
+    __shared__ int last;
     const long per_block = (n + gridDim.x - 1) / gridDim.x;
     const long lo = (long)blockIdx.x * per_block;
     const long hi = min(n, lo + per_block);
@@ -109,18 +124,16 @@ k_sumsq_partial(const D *__restrict__ x, long n, double *__restrict__ partials)
         if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
         __syncthreads();
     }
-    if (threadIdx.x == 0) partials[blockIdx.x] = sh[0];
-}
-
-// one warp, fixed order: lane l adds partials l, l+32, ... in sequence, then a fixed shuffle tree
-__global__ void k_sum_final(const double *__restrict__ partials, int nb, double *out)
-{
-    const int lane = threadIdx.x;
-    double s = 0.0;
-    for (int b = lane; b < nb; b += 32) s += partials[b];
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) s += shfl_xor_d(s, m);
-    if (lane == 0) *out = s;
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = sh[0];
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (threadIdx.x < 32) sum_final_warp(partials, (int)gridDim.x, out);
+    if (threadIdx.x == 0) *ticket = 0u;
 }
 
 constexpr int kHistMaxBins = 8192;  // 32 KB of shared counters per block
@@ -175,7 +188,8 @@ k_select_count(const int *__restrict__ assign, long n, int cid, long per_block,
 // pass 2 (one block): find the counting block holding the kth member, then the member in it
 __global__ void __launch_bounds__(1024)
 k_select_pick(const int32_t *__restrict__ assign, long n, int32_t cid, long kth, long per_block,
-              const unsigned long long *block_counts, int nb, int64_t *out)
+              const unsigned long long *block_counts, int nb, int64_t *out, long offset,
+              int64_t *global_out)
 {
     // One block of 1024 threads; every load of a phase is independent of the others (the first
     // version walked 31 + 32 dependent 32-wide steps with one warp: 11 us per proposal).
@@ -219,7 +233,10 @@ k_select_pick(const int32_t *__restrict__ assign, long n, int32_t cid, long kth,
     }
     __syncthreads();
     if (s_block >= nb) {
-        if (tid == 0) *out = -1;
+        if (tid == 0) {
+            *out = -1;
+            if (global_out) *global_out = -1;
+        }
         return;
     }
     // ---- phase 2: the (rem)-th member inside that block's range -----------------------------
@@ -240,12 +257,18 @@ k_select_pick(const int32_t *__restrict__ assign, long n, int32_t cid, long kth,
             total += c;
         }
         if (rem < total) {
-            if (hit && pre + __popc(mask & ((1u << lane) - 1u)) == rem) *out = i;
+            if (hit && pre + __popc(mask & ((1u << lane) - 1u)) == rem) {
+                *out = i;
+                if (global_out) *global_out = i + offset;   // GLOBAL frame index of the member
+            }
             return;
         }
         rem -= total;
     }
-    if (tid == 0) *out = -1;
+    if (tid == 0) {
+        *out = -1;
+        if (global_out) *global_out = -1;
+    }
 }
 
 // The proposal takes medoid cid's slot, the displaced medoid is kept for a rejection
@@ -274,11 +297,6 @@ __global__ void k_restore_slot(float *slot, double *slot_trace, const float *sav
     if (threadIdx.x == 0) *slot_trace = *saved_trace;
 }
 
-__global__ void k_global_index(const int64_t *local, int64_t offset, int64_t *out)
-{
-    out[0] = local[0] + offset;
-}
-
 // ------------------------------------------------------------------------------------------
 // Re-assignment of a proposal's ambiguous frames (kmedoids.py:666-670) against the medoids the
 // triangle inequality leaves.  RMSD is a metric: d(x, m_j) >= d(p, m_j) - d(x, p), so medoid j
@@ -292,14 +310,40 @@ __global__ void k_global_index(const int64_t *local, int64_t offset, int64_t *ou
 // lanes, same atom order, same QCP) by the warp's four 8-lane groups; the nearest of those and
 // (d(x, p), cid) wins, lowest index on ties.
 // ------------------------------------------------------------------------------------------
+struct SlotExchange {            // k_take_slot's arguments, for the kernels that fold it in
+    float *slot;
+    double *slot_trace;
+    float *saved;
+    double *saved_trace;
+    const float *prop;
+    const double *prop_trace;
+    long frame_floats;
+    int64_t *scal_i;
+    const int64_t *prop_idx;
+};
+
 __global__ void __launch_bounds__(1024)
 k_pam_medoid_list(const int64_t *__restrict__ ambig_idx, const int64_t *__restrict__ n_ambig,
                   const float *__restrict__ new_ctr_dist, const float *__restrict__ cc, int k,
-                  int cid, int cap, int32_t *list, int32_t *list_n, int32_t *ovf)
+                  int cid, int cap, int32_t *list, int32_t *list_n, int32_t *ovf,
+                  SlotExchange ex)
 {
     __shared__ float s_max[32];
     __shared__ int s_cnt[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (ex.slot) {
+        // the slot exchange of k_take_slot rides along (the listed re-assignment never reads
+        // slot cid: the proposal's distances are new_ctr_dist)
+        for (long i = tid; i < ex.frame_floats; i += 1024) {
+            ex.saved[i] = ex.slot[i];
+            ex.slot[i] = ex.prop[i];
+        }
+        if (tid == 0) {
+            *ex.saved_trace = *ex.slot_trace;
+            *ex.slot_trace = *ex.prop_trace;
+            ex.scal_i[0] = ex.prop_idx[0];
+        }
+    }
     const long m = (long)*n_ambig;
     float dmax = 0.0f;
     for (long p = tid; p < m; p += 1024) dmax = fmaxf(dmax, new_ctr_dist[ambig_idx[p]]);
@@ -482,7 +526,7 @@ extern "C" {
 size_t eb_pam_scratch_bytes(int64_t n)
 {
     (void)n;
-    return sizeof(double) * kPamMaxBlocks;
+    return sizeof(double) * kPamMaxBlocks + 16;   // partials / block counts + the ticket
 }
 
 int eb_pam_classify(const void *new_ctr_dist, const void *dist, const int32_t *assign, int64_t n,
@@ -532,14 +576,13 @@ int eb_sum_squares(const void *dist, int64_t n, int dist_is_f64, double *out, vo
         return EB_OK;
     }
     const int nb = pam_blocks(n);
+    unsigned int *ticket = reinterpret_cast<unsigned int *>((double *)scratch + kPamMaxBlocks);
     if (dist_is_f64)
-        k_sumsq_partial<double><<<nb, kPamThreads, 0, s>>>((const double *)dist, n,
-                                                           (double *)scratch);
+        k_sumsq<double><<<nb, kPamThreads, 0, s>>>((const double *)dist, n, (double *)scratch,
+                                                   ticket, out);
     else
-        k_sumsq_partial<float><<<nb, kPamThreads, 0, s>>>((const float *)dist, n,
-                                                          (double *)scratch);
-    EB_LAUNCH_CHECK();
-    k_sum_final<<<1, 32, 0, s>>>((const double *)scratch, nb, out);
+        k_sumsq<float><<<nb, kPamThreads, 0, s>>>((const float *)dist, n, (double *)scratch,
+                                                  ticket, out);
     EB_LAUNCH_CHECK();
     return EB_OK;
 }
@@ -563,8 +606,8 @@ int eb_count_members(const int32_t *assign, int64_t n, int32_t k, int64_t *count
     return EB_OK;
 }
 
-int eb_select_member(const int32_t *assign, int64_t n, int32_t cid, int64_t kth, int64_t *out,
-                     void *scratch, void *stream)
+static int select_member(const int32_t *assign, int64_t n, int32_t cid, int64_t kth, int64_t *out,
+                         void *scratch, int64_t offset, int64_t *global_out, void *stream)
 {
     EB_CHECK_ARG(n >= 0 && kth >= 0 && out && scratch, "select_member: bad arguments");
     cudaStream_t s = (cudaStream_t)stream;
@@ -574,9 +617,16 @@ int eb_select_member(const int32_t *assign, int64_t n, int32_t cid, int64_t kth,
                                               (unsigned long long *)scratch);
     EB_LAUNCH_CHECK();
     k_select_pick<<<1, 1024, 0, s>>>(assign, n, cid, kth, per_block,
-                                   (const unsigned long long *)scratch, nb, out);
+                                     (const unsigned long long *)scratch, nb, out, (long)offset,
+                                     global_out);
     EB_LAUNCH_CHECK();
     return EB_OK;
+}
+
+int eb_select_member(const int32_t *assign, int64_t n, int32_t cid, int64_t kth, int64_t *out,
+                     void *scratch, void *stream)
+{
+    return select_member(assign, n, cid, kth, out, scratch, 0, nullptr, stream);
 }
 
 int eb_pam_propose_rmsd(const eb_pam_ctx *c, int32_t cid, int64_t kth, int64_t m_max, int stages,
@@ -590,50 +640,76 @@ int eb_pam_propose_rmsd(const eb_pam_ctx *c, int32_t cid, int64_t kth, int64_t m
     const size_t frame_floats = 3 * (size_t)rmsd_apad(c->n_atoms);
     int rc;
     if (stages & EB_PAM_SELECT) {
-        rc = eb_select_member(c->assign, c->n, cid, kth, c->scal_i, c->scratch, stream);
+        // k-th member of the cluster -> scal_i[0] (local) and prop_idx (global), then its frame
+        rc = select_member(c->assign, c->n, cid, kth, c->scal_i, c->scratch, c->frame_offset,
+                           c->prop_idx, stream);
         if (rc != EB_OK) return rc;
         rc = eb_gather_frames(c->xyz, c->traces, c->n_atoms, c->scal_i, 1, c->prop_xyz,
                               c->prop_traces, stream);
         if (rc != EB_OK) return rc;
-        k_global_index<<<1, 1, 0, s>>>(c->scal_i, c->frame_offset, c->prop_idx);
-        EB_LAUNCH_CHECK();
     }
     if (stages & EB_PAM_TRIAL) {
         EB_CHECK_ARG(c->dist && c->assign && c->new_dist && c->new_assign && c->new_ctr_dist &&
                          c->cc && c->need_idx && c->need_n && c->need_assign && c->ambig_idx &&
                          c->saved_xyz,
                      "pam_propose: missing buffers");
+        // the three device counters of a proposal {n_ambig, overflow, n_need} are cleared with
+        // one memset when the caller laid them out next to each other
+        const bool counters_adjacent =
+            c->tc_ovf && (const char *)c->tc_ovf == (const char *)(c->scal_i + 2) &&
+            (const char *)c->need_n == (const char *)(c->scal_i + 3);
+        if (counters_adjacent) {
+            EB_CUDA(cudaMemsetAsync(c->scal_i + 1, 0, 3 * sizeof(int64_t), s));
+        } else {
+            EB_CUDA(cudaMemsetAsync(c->scal_i + 1, 0, sizeof(int64_t), s));
+            EB_CUDA(cudaMemsetAsync(c->need_n, 0, sizeof(int64_t), s));
+            if (c->tc_ovf) EB_CUDA(cudaMemsetAsync(c->tc_ovf, 0, sizeof(int32_t), s));
+        }
         // distances proposal -> every medoid, then the pruned full pass (kmedoids.py:637)
         rc = eb_rmsd_one_to_all(c->medoid_xyz, c->medoid_traces, c->k, c->n_atoms, c->prop_xyz,
                                 c->prop_traces, c->cc, 1, stream);
         if (rc != EB_OK) return rc;
-        rc = eb_pam_need_list(c->dist, c->assign, c->cc, c->n, cid, c->new_ctr_dist, c->need_idx,
-                              c->need_n, stream);
-        if (rc != EB_OK) return rc;
         if (c->n > 0) {
+            k_pam_need_list<<<pam_blocks(c->n), kPamThreads, 0, s>>>(
+                c->dist, c->assign, c->cc, c->n, cid, c->new_ctr_dist, c->need_idx,
+                (unsigned long long *)c->need_n);
+            EB_LAUNCH_CHECK();
             rc = eb_rmsd_assign_dev(c->xyz, c->traces, c->n, c->n_atoms, c->prop_xyz,
                                     c->prop_traces, 1, c->need_idx, c->n, c->new_ctr_dist,
                                     c->need_assign, 0, 1, (const int32_t *)c->need_n, stream);
             if (rc != EB_OK) return rc;
+            // three-way split (kmedoids.py:644-658)
+            k_pam_classify<float><<<pam_blocks(c->n), kPamThreads, 0, s>>>(
+                c->new_ctr_dist, c->dist, c->assign, c->n, cid, c->new_dist, c->new_assign,
+                c->ambig_idx, (unsigned long long *)(c->scal_i + 1));
+            EB_LAUNCH_CHECK();
         }
-        // three-way split (kmedoids.py:644-658)
-        rc = eb_pam_classify(c->new_ctr_dist, c->dist, c->assign, c->n, 0, cid, c->new_dist,
-                             c->new_assign, c->ambig_idx, c->scal_i + 1, stream);
-        if (rc != EB_OK) return rc;
         // the proposal takes the medoid's slot (kmedoids.py:660-664); the old one is kept
-        k_take_slot<<<1, 512, 0, s>>>(c->medoid_xyz + (size_t)cid * frame_floats,
-                                      c->medoid_traces + cid, c->saved_xyz, c->saved_traces,
-                                      c->prop_xyz, c->prop_traces, (long)frame_floats, c->scal_i,
-                                      c->prop_idx, c->tc_ovf);
-        EB_LAUNCH_CHECK();
+        SlotExchange ex;
+        ex.slot = c->medoid_xyz + (size_t)cid * frame_floats;
+        ex.slot_trace = c->medoid_traces + cid;
+        ex.saved = c->saved_xyz;
+        ex.saved_trace = c->saved_traces;
+        ex.prop = c->prop_xyz;
+        ex.prop_trace = c->prop_traces;
+        ex.frame_floats = (long)frame_floats;
+        ex.scal_i = c->scal_i;
+        ex.prop_idx = c->prop_idx;
+        const bool listed = m_max > 0 && c->use_list;
+        if (!listed) {
+            k_take_slot<<<1, 512, 0, s>>>(ex.slot, ex.slot_trace, ex.saved, ex.saved_trace, ex.prop,
+                                          ex.prop_trace, ex.frame_floats, ex.scal_i, ex.prop_idx,
+                                          nullptr);
+            EB_LAUNCH_CHECK();
+        }
         // ambiguous frames against all medoids (kmedoids.py:666-670)
-        if (m_max > 0 && c->use_list) {
+        if (listed) {
             EB_CHECK_ARG(c->med_list && c->med_list_n && c->med_list_cap > 0 && c->tc_ovf &&
                              c->med_list_cap <= 2048,
                          "pam_propose: missing medoid list");
             k_pam_medoid_list<<<1, 1024, 0, s>>>(c->ambig_idx, c->scal_i + 1, c->new_ctr_dist,
                                                  c->cc, c->k, cid, c->med_list_cap, c->med_list,
-                                                 c->med_list_n, c->tc_ovf);
+                                                 c->med_list_n, c->tc_ovf, ex);
             EB_LAUNCH_CHECK();
             long blocks = (m_max + kListWarps - 1) / kListWarps;
             if (blocks > 4L * sm_count()) blocks = 4L * sm_count();

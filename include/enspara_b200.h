@@ -284,6 +284,9 @@ int eb_pam_classify(const void *new_ctr_dist, const void *dist, const int32_t *a
  * pass. */
 int eb_pam_need_list(const float *dist, const int32_t *assign, const float *cc, int64_t n,
                      int32_t cid, float *out, int64_t *need_idx, int64_t *n_need, void *stream);
+/* scratch of eb_sum_squares / eb_select_member: eb_pam_scratch_bytes(n) bytes, ZERO-INITIALISED
+ * once by the caller (eb_sum_squares keeps a ticket counter behind its partial sums and leaves
+ * it zero) */
 size_t eb_pam_scratch_bytes(int64_t n);
 int eb_sum_squares(const void *dist, int64_t n, int dist_is_f64, double *out, void *scratch,
                    void *stream);
