@@ -144,10 +144,13 @@ def test_determine_batch_size_bounds(monkeypatch):
     largest file while that still fits the hard (RAM / HBM) bound."""
     import types
     import psutil
+    import torch
     monkeypatch.setattr(psutil, "virtual_memory",
                         lambda: types.SimpleNamespace(total=64 << 30))
+    # the RAM bound alone, whether or not the box running this has a GPU
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: False)
     bpf = 500 * 3 * 4
-    hard = int((64 << 30) * 0.5 / 2 / bpf)              # no CUDA here: RAM bound only
+    hard = int((64 << 30) * 0.5 / 2 / bpf)
     n, gb = rz.determine_batch_size(500, 4, 0.5)
     assert n == min(hard, rz.BATCH_BYTES_CAP // bpf) and abs(gb - n * bpf / 2 ** 30) < 1e-9
     big = rz.BATCH_BYTES_CAP // bpf + 1000              # a file larger than the soft cap
@@ -155,3 +158,8 @@ def test_determine_batch_size_bounds(monkeypatch):
     assert n2 == big
     n3, _ = rz.determine_batch_size(500, 4, 0.5, largest_file=10 * hard)
     assert n3 == hard                                   # ... but never beyond the hard bound
+    # with a device: a quarter of the free HBM over 3x the host bytes per frame bounds it too
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "mem_get_info", lambda: (24 << 30, 180 << 30))
+    n4, _ = rz.determine_batch_size(500, 4, 0.5, largest_file=10 * hard)
+    assert n4 == int((24 << 30) * 0.25 / (3 * bpf)) < hard
